@@ -1,0 +1,98 @@
+/* roko_b200 -- C ABI of the B200-native replacement for roko's inference hot path.
+ *
+ * The reference implements this path in Python on top of PyTorch (roko/rnn_model.py `RNN`,
+ * called from roko/inference.py:110-117); it has no FFI of its own for it.  The entry points
+ * below are what a binding for that path needs, one per reference call site; a Python binding
+ * (ctypes, roko_b200/_cabi.py) and the drop-in `RNN` class built on it (roko_b200/rnn_model.py)
+ * ship in this repo, and INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * ROKO_B200_E* code, with a human-readable message available from roko_b200_last_error()
+ * (thread local).  Device pointers must belong to the model's device.  Nothing here
+ * synchronises the stream unless stated; work is enqueued on the `stream` argument
+ * (a cudaStream_t / CUstream passed as void*, NULL = legacy default stream).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef ROKO_B200_H
+#define ROKO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROKO_B200_ABI_VERSION 1
+
+#define ROKO_B200_OK 0
+#define ROKO_B200_EARG 1     /* bad argument (null pointer, bad size, misaligned buffer) */
+#define ROKO_B200_ECUDA 2    /* a CUDA runtime call failed; message carries cudaGetErrorString */
+#define ROKO_B200_ESTATE 3   /* model has no weights loaded */
+#define ROKO_B200_ECODES 4   /* an input code was outside 0..11 (nn.Embedding would raise IndexError) */
+
+typedef struct roko_b200_model roko_b200_model;
+
+int roko_b200_abi_version(void);
+const char* roko_b200_last_error(void);
+
+/* Geometry of the path (reference include/generate.h:19; roko/rnn_model.py:10-12,28-44). */
+int roko_b200_window_reads(void);        /* 200 */
+int roko_b200_window_cols(void);         /* 90  */
+int roko_b200_num_classes(void);         /* 5   */
+size_t roko_b200_raw_weight_count(void); /* 1 099 731 fp32 = the 31 state_dict tensors, in order */
+
+/* Bytes of device scratch a forward over `max_windows` windows wants.  A smaller buffer is legal:
+ * forward then walks the batch in chunks that fit (at least one window must fit). */
+size_t roko_b200_workspace_bytes(int max_windows);
+
+/* RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)        -- roko/inference.py:94, rnn_model.py:25-44 */
+int roko_b200_model_create(roko_b200_model** out, int device);
+/* model.load_state_dict(torch.load(path))                 -- roko/inference.py:95
+ * `raw` holds the 31 tensors flattened in state_dict order, host or device
+ * memory.  Repacks them into the kernels' layouts; call again whenever the parameters change.
+ * Synchronises `stream` (it reads back the 87 KB the front-end kernel takes as parameters). */
+int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device, void* stream);
+int roko_b200_model_destroy(roko_b200_model* m);
+
+/* logits = model(x); Y = argmax(logits, 2)                -- roko/rnn_model.py:46-59, inference.py:115-116
+ * x: device, (n_windows, 200, 90) codes 0..11, contiguous, 16-byte aligned.
+ * logits (n_windows, 90, 5) fp32 and labels (n_windows, 90) uint8 are device buffers; either may
+ * be NULL.  The u8 form is the native one (the .hdf5 dtype, reference roko/data.py:48); the i64
+ * form accepts what the reference caller builds at inference.py:113. */
+int roko_b200_forward_u8(roko_b200_model* m, const uint8_t* x, int n_windows, float* logits,
+                         uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream);
+int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, float* logits,
+                          uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The loop body of roko/inference.py:111-117 for HOST buffers: for each batch of `batch` windows
+ * copy x to the device, run the path, copy labels (and logits if not NULL) back.  Batches are
+ * pipelined over internal streams; returns after everything has landed in the host buffers.
+ * Pinned host memory makes the copies asynchronous. */
+int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_windows, int batch,
+                         uint8_t* labels_host, float* logits_host);
+
+/* Synchronises the device and reports sticky input errors seen by earlier forwards
+ * (bit 0: code outside 0..11), then clears them.  Returns ROKO_B200_ECODES if any were set. */
+int roko_b200_model_check(roko_b200_model* m);
+
+/* Stage taps for parity tests: run the path over n_windows (<= what fits the workspace) and copy
+ * out intermediate device buffers.  Any pointer may be NULL.
+ *   front (n,90,500)   gru[l] (n,90,256) for l = 0..2  */
+int roko_b200_forward_taps(roko_b200_model* m, const uint8_t* x, int n_windows, float* front,
+                           float* gru0, float* gru1, float* gru2, float* logits, uint8_t* labels,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement helpers used by bench.py (not part of the reference's interface).
+ * forward_timed: `iters` forwards of one chunk with CUDA events between the 8 kernels of the chain
+ *   (front, proj0, rec0, proj1, rec1, proj2, rec2, head); stage_ms[8] = mean milliseconds each.
+ * measure_fp32_peak: dependent-free FFMA loop on every SM, best of 5, TFLOP/s. */
+int roko_b200_forward_timed(roko_b200_model* m, const uint8_t* x, int n_windows, uint8_t* labels,
+                            void* workspace, size_t workspace_bytes, void* stream, int iters,
+                            float* stage_ms);
+int roko_b200_measure_fp32_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROKO_B200_H */

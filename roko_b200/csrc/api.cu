@@ -1,0 +1,338 @@
+// C ABI of libroko_b200 (include/roko_b200.h): model lifetime, weight packing, the forward pass
+// as a chain of kernels on the caller's stream, and the pipelined host-buffer loop.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/roko_b200.h"
+#include "common.cuh"
+
+using namespace roko;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return fail(ROKO_B200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr size_t WIN_BYTES = (size_t)READS * COLS;                  // 18 000
+constexpr size_t WS_WIN_BYTES = WS_PER_WINDOW * sizeof(float) + WIN_BYTES;
+constexpr int NSLOT = 3;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct roko_b200_model {
+    int device = 0;
+    int num_sms = 148;
+    float* packed = nullptr;
+    float* raw_stage = nullptr;
+    int* status = nullptr;          // device flag word, bit 0: code outside 0..11
+    bool loaded = false;
+    FrontConst fc;
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        uint8_t* x = nullptr;
+        uint8_t* labels = nullptr;
+        float* logits = nullptr;
+        void* ws = nullptr;
+    } slot[NSLOT];
+    int slot_cap = 0;
+};
+
+namespace {
+
+struct Taps { float *front, *gru[3]; };
+
+// One chunked pass over n windows; everything is enqueued on `s`.
+int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint8_t* labels, void* ws,
+                size_t ws_bytes, cudaStream_t s, const Taps* taps, size_t per_window_bytes,
+                cudaEvent_t* ev = nullptr) {
+    const long long cap_ll = (long long)(ws_bytes / per_window_bytes);
+    if (cap_ll < 1) return fail(ROKO_B200_EARG, "workspace smaller than one window%s%s");
+    const int cap = cap_ll > n ? n : (int)cap_ll;
+    if (taps && cap < n) return fail(ROKO_B200_EARG, "forward_taps needs the whole batch in the workspace%s%s");
+    float* u = static_cast<float*>(ws);
+    float* gi = u + (size_t)cap * WS_U;
+    float* h0 = gi + (size_t)cap * WS_GI;
+    float* h1 = h0 + (size_t)cap * WS_H;
+    const float* pk = m->packed;
+    const size_t dstride = (size_t)(pk_whh(0, 1) - pk_whh(0, 0));
+
+    for (int c0 = 0; c0 < n; c0 += cap) {
+        const int nc = (n - c0) < cap ? (n - c0) : cap;
+        const int rows = nc * COLS;
+        if (ev) CU(cudaEventRecord(ev[0], s));
+        CU(launch_front(m->fc, x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
+        if (taps && taps->front)
+            CU(cudaMemcpy2DAsync(taps->front, IN0 * sizeof(float), u, IN0P * sizeof(float), IN0 * sizeof(float),
+                                 rows, cudaMemcpyDeviceToDevice, s));
+        const float* in = u;
+        float* outs[3] = {h0, h1, h0};
+        for (int l = 0; l < LAYERS; ++l) {
+            if (ev) CU(cudaEventRecord(ev[1 + 2 * l], s));
+            CU(launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s));
+            if (ev) CU(cudaEventRecord(ev[2 + 2 * l], s));
+            CU(launch_rec(gi, pk + pk_whh(l, 0), dstride, pk + pk_bhn(l, 0), outs[l], nc, m->num_sms, s));
+            if (taps && taps->gru[l])
+                CU(cudaMemcpyAsync(taps->gru[l], outs[l], (size_t)rows * OUT_W * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+            in = outs[l];
+        }
+        if (ev) CU(cudaEventRecord(ev[7], s));
+        CU(launch_head(in, pk + PK_W4, pk + PK_B4, logits ? logits + (size_t)c0 * COLS * CLASSES : nullptr,
+                       labels ? labels + (size_t)c0 * COLS : nullptr, rows, s));
+        if (ev) CU(cudaEventRecord(ev[8], s));
+    }
+    return ROKO_B200_OK;
+}
+
+int check_common(roko_b200_model* m, const void* x, int n, void* ws) {
+    if (!m) return fail(ROKO_B200_EARG, "model is NULL%s%s");
+    if (!m->loaded) return fail(ROKO_B200_ESTATE, "no weights loaded (call roko_b200_model_load)%s%s");
+    if (n < 0) return fail(ROKO_B200_EARG, "n_windows < 0%s%s");
+    if (n > 0 && (!x || !ws)) return fail(ROKO_B200_EARG, "x / workspace is NULL%s%s");
+    if (((uintptr_t)x & 15) || ((uintptr_t)ws & 15)) return fail(ROKO_B200_EARG, "x / workspace must be 16-byte aligned%s%s");
+    return ROKO_B200_OK;
+}
+
+int ensure_slots(roko_b200_model* m, int batch) {
+    if (m->slot_cap >= batch) return ROKO_B200_OK;
+    for (auto& sl : m->slot) {
+        if (!sl.stream) CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        cudaFree(sl.x); cudaFree(sl.labels); cudaFree(sl.logits); cudaFree(sl.ws);
+        sl.x = nullptr; sl.labels = nullptr; sl.logits = nullptr; sl.ws = nullptr;
+        CU(cudaMalloc(&sl.x, (size_t)batch * WIN_BYTES));
+        CU(cudaMalloc(&sl.labels, (size_t)batch * COLS));
+        CU(cudaMalloc(&sl.logits, (size_t)batch * COLS * CLASSES * sizeof(float)));
+        CU(cudaMalloc(&sl.ws, (size_t)batch * WS_WIN_BYTES));
+    }
+    m->slot_cap = batch;
+    return ROKO_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int roko_b200_abi_version(void) { return ROKO_B200_ABI_VERSION; }
+const char* roko_b200_last_error(void) { return g_err; }
+int roko_b200_window_reads(void) { return READS; }
+int roko_b200_window_cols(void) { return COLS; }
+int roko_b200_num_classes(void) { return CLASSES; }
+size_t roko_b200_raw_weight_count(void) { return RAW_TOTAL; }
+
+size_t roko_b200_workspace_bytes(int max_windows) {
+    return max_windows < 1 ? WS_WIN_BYTES : (size_t)max_windows * WS_WIN_BYTES;
+}
+
+int roko_b200_model_create(roko_b200_model** out, int device) {
+    if (!out) return fail(ROKO_B200_EARG, "out is NULL%s%s");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(ROKO_B200_EARG, "no such CUDA device%s%s");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ROKO_B200_ECUDA, "cudaSetDevice failed%s%s");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(ROKO_B200_ECUDA, "libroko_b200 is built for sm_100a only; device is %s%s", prop.name);
+    roko_b200_model* m = new (std::nothrow) roko_b200_model();
+    if (!m) return fail(ROKO_B200_EARG, "out of host memory%s%s");
+    m->device = device;
+    m->num_sms = prop.multiProcessorCount;
+    cudaError_t e = cudaMalloc(&m->packed, (size_t)PK_TOTAL * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->raw_stage, (size_t)RAW_TOTAL * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
+    if (e == cudaSuccess) e = front_setup();
+    if (e == cudaSuccess) e = rec_setup();
+    if (e != cudaSuccess) {
+        roko_b200_model_destroy(m);
+        return fail(ROKO_B200_ECUDA, "model_create: %s%s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return ROKO_B200_OK;
+}
+
+int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device, void* stream) {
+    if (!m || !raw) return fail(ROKO_B200_EARG, "model / raw is NULL%s%s");
+    DeviceGuard g(m->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float* src = raw;
+    if (!raw_on_device) {
+        CU(cudaMemcpyAsync(m->raw_stage, raw, (size_t)RAW_TOTAL * sizeof(float), cudaMemcpyHostToDevice, s));
+        src = m->raw_stage;
+    }
+    CU(launch_pack(src, m->packed, s));
+    // W2 / b1 / b2 ride in the front-end kernel's parameter bank: keep a host copy
+    if (raw_on_device) {
+        CU(cudaMemcpyAsync(m->fc.W2, raw + RAW_W2, sizeof(m->fc.W2), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(m->fc.b1, raw + RAW_B1, sizeof(m->fc.b1), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(m->fc.b2, raw + RAW_B2, sizeof(m->fc.b2), cudaMemcpyDeviceToHost, s));
+    } else {
+        memcpy(m->fc.W2, raw + RAW_W2, sizeof(m->fc.W2));
+        memcpy(m->fc.b1, raw + RAW_B1, sizeof(m->fc.b1));
+        memcpy(m->fc.b2, raw + RAW_B2, sizeof(m->fc.b2));
+    }
+    CU(cudaStreamSynchronize(s));
+    m->loaded = true;
+    return ROKO_B200_OK;
+}
+
+int roko_b200_model_destroy(roko_b200_model* m) {
+    if (!m) return ROKO_B200_OK;
+    DeviceGuard g(m->device);
+    for (auto& sl : m->slot) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        if (sl.done) cudaEventDestroy(sl.done);
+        cudaFree(sl.x); cudaFree(sl.labels); cudaFree(sl.logits); cudaFree(sl.ws);
+    }
+    cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->status);
+    delete m;
+    return ROKO_B200_OK;
+}
+
+int roko_b200_forward_u8(roko_b200_model* m, const uint8_t* x, int n_windows, float* logits,
+                         uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_common(m, x, n_windows, workspace)) return rc;
+    if (n_windows == 0) return ROKO_B200_OK;
+    DeviceGuard g(m->device);
+    return run_forward(m, x, n_windows, logits, labels, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), nullptr, WS_PER_WINDOW * sizeof(float));
+}
+
+int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, float* logits,
+                          uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_common(m, x, n_windows, workspace)) return rc;
+    if (n_windows == 0) return ROKO_B200_OK;
+    DeviceGuard g(m->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long cap_ll = (long long)(workspace_bytes / WS_WIN_BYTES);
+    if (cap_ll < 1) return fail(ROKO_B200_EARG, "workspace smaller than one window%s%s");
+    const int cap = cap_ll > n_windows ? n_windows : (int)cap_ll;
+    // the narrowed copy of a chunk lives behind the fp32 scratch of that chunk
+    uint8_t* x8 = static_cast<uint8_t*>(workspace) + (size_t)cap * WS_PER_WINDOW * sizeof(float);
+    for (int c0 = 0; c0 < n_windows; c0 += cap) {
+        const int nc = (n_windows - c0) < cap ? (n_windows - c0) : cap;
+        CU(launch_narrow_i64(reinterpret_cast<const long long*>(x) + (size_t)c0 * WIN_BYTES, x8,
+                             (size_t)nc * WIN_BYTES, m->status, s));
+        int rc = run_forward(m, x8, nc, logits ? logits + (size_t)c0 * COLS * CLASSES : nullptr,
+                             labels ? labels + (size_t)c0 * COLS : nullptr, workspace,
+                             (size_t)cap * WS_PER_WINDOW * sizeof(float), s, nullptr,
+                             WS_PER_WINDOW * sizeof(float));
+        if (rc) return rc;
+    }
+    return ROKO_B200_OK;
+}
+
+int roko_b200_forward_taps(roko_b200_model* m, const uint8_t* x, int n_windows, float* front, float* gru0,
+                           float* gru1, float* gru2, float* logits, uint8_t* labels, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (int rc = check_common(m, x, n_windows, workspace)) return rc;
+    if (n_windows == 0) return ROKO_B200_OK;
+    DeviceGuard g(m->device);
+    Taps t{front, {gru0, gru1, gru2}};
+    return run_forward(m, x, n_windows, logits, labels, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream), &t, WS_PER_WINDOW * sizeof(float));
+}
+
+int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_windows, int batch,
+                         uint8_t* labels_host, float* logits_host) {
+    if (!m) return fail(ROKO_B200_EARG, "model is NULL%s%s");
+    if (!m->loaded) return fail(ROKO_B200_ESTATE, "no weights loaded (call roko_b200_model_load)%s%s");
+    if (n_windows < 0 || batch < 1) return fail(ROKO_B200_EARG, "bad n_windows / batch%s%s");
+    if (n_windows == 0) return ROKO_B200_OK;
+    if (!x_host || !labels_host) return fail(ROKO_B200_EARG, "x_host / labels_host is NULL%s%s");
+    DeviceGuard g(m->device);
+    if (int rc = ensure_slots(m, batch)) return rc;
+    int i = 0;
+    for (long long b0 = 0; b0 < n_windows; b0 += batch, ++i) {
+        const int nb = (n_windows - b0) < batch ? (int)(n_windows - b0) : batch;
+        auto& sl = m->slot[i % NSLOT];
+        // stream order already protects the slot's device buffers against the previous use
+        CU(cudaMemcpyAsync(sl.x, x_host + (size_t)b0 * WIN_BYTES, (size_t)nb * WIN_BYTES, cudaMemcpyHostToDevice, sl.stream));
+        int rc = run_forward(m, sl.x, nb, logits_host ? sl.logits : nullptr, sl.labels, sl.ws,
+                             (size_t)m->slot_cap * WS_WIN_BYTES, sl.stream, nullptr, WS_PER_WINDOW * sizeof(float));
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(labels_host + (size_t)b0 * COLS, sl.labels, (size_t)nb * COLS, cudaMemcpyDeviceToHost, sl.stream));
+        if (logits_host)
+            CU(cudaMemcpyAsync(logits_host + (size_t)b0 * COLS * CLASSES, sl.logits,
+                               (size_t)nb * COLS * CLASSES * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (auto& sl : m->slot) CU(cudaStreamSynchronize(sl.stream));
+    return ROKO_B200_OK;
+}
+
+int roko_b200_forward_timed(roko_b200_model* m, const uint8_t* x, int n_windows, uint8_t* labels,
+                            void* workspace, size_t workspace_bytes, void* stream, int iters, float* stage_ms) {
+    if (int rc = check_common(m, x, n_windows, workspace)) return rc;
+    if (n_windows < 1 || iters < 1 || !stage_ms) return fail(ROKO_B200_EARG, "bad n_windows / iters / stage_ms%s%s");
+    if ((size_t)n_windows * WS_PER_WINDOW * sizeof(float) > workspace_bytes)
+        return fail(ROKO_B200_EARG, "forward_timed needs the whole batch in the workspace%s%s");
+    DeviceGuard g(m->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev[9];
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    for (int k = 0; k < 8; ++k) stage_ms[k] = 0.f;
+    int rc = ROKO_B200_OK;
+    for (int it = 0; it < iters && rc == ROKO_B200_OK; ++it) {
+        rc = run_forward(m, x, n_windows, nullptr, labels, workspace, workspace_bytes, s, nullptr,
+                         WS_PER_WINDOW * sizeof(float), ev);
+        if (rc) break;
+        CU(cudaStreamSynchronize(s));
+        for (int k = 0; k < 8; ++k) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            stage_ms[k] += ms / iters;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int roko_b200_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(ROKO_B200_EARG, "tflops is NULL%s%s");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(ROKO_B200_ECUDA, "cudaSetDevice failed%s%s");
+    double best = 0.0;
+    CU(measure_fp32_peak(&best));
+    *tflops = best;
+    return ROKO_B200_OK;
+}
+
+int roko_b200_model_check(roko_b200_model* m) {
+    if (!m) return fail(ROKO_B200_EARG, "model is NULL%s%s");
+    DeviceGuard g(m->device);
+    CU(cudaDeviceSynchronize());
+    int st = 0;
+    CU(cudaMemcpy(&st, m->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        CU(cudaMemset(m->status, 0, sizeof(int)));
+        return fail(ROKO_B200_ECODES, "input code outside 0..11 (index out of range in embedding)%s%s");
+    }
+    return ROKO_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Shared constants, packed-weight layout and small device helpers for the roko hot path.
+//
+// Geometry follows the reference: a window is 200 sampled reads x 90 pileup columns of uint8
+// codes 0..11 (reference include/generate.h:19, generate.cpp:18-25,145); the network is
+// roko/rnn_model.py:24-59 (embedding 12x50, fc1 200->100 over the READ axis, fc2 100->10,
+// 3-layer bidirectional GRU hidden 128, fc4 256->5).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace roko {
+
+constexpr int READS = 200;     // generate.h:19
+constexpr int COLS = 90;       // generate.h:19  (GRU time axis, rnn_model.py:56)
+constexpr int NCODES = 12;     // rnn_model.py:28
+constexpr int EMB = 50;        // rnn_model.py:28
+constexpr int FC1 = 100;       // rnn_model.py:31
+constexpr int FC2 = 10;        // rnn_model.py:34
+constexpr int IN0 = 500;       // rnn_model.py:10
+constexpr int IN0P = 512;      // IN0 padded to a multiple of the GEMM k-tile (pad columns are zero)
+constexpr int HID = 128;       // rnn_model.py:11
+constexpr int G3 = 3 * HID;    // gate rows per direction, reference order [r; z; n]
+constexpr int GI_N = 2 * G3;   // both directions
+constexpr int LAYERS = 3;      // rnn_model.py:12
+constexpr int OUT_W = 2 * HID; // [fwd ; bwd]
+constexpr int CLASSES = 5;     // rnn_model.py:44
+
+// ---- raw weights: the 31 state_dict tensors of the reference module, flattened in state_dict
+// ---- order, fp32 ----------------------------------------------------------
+constexpr int RAW_E = 0;
+constexpr int RAW_W1 = RAW_E + NCODES * EMB;     // (100,200)
+constexpr int RAW_B1 = RAW_W1 + FC1 * READS;
+constexpr int RAW_W2 = RAW_B1 + FC1;             // (10,100)
+constexpr int RAW_B2 = RAW_W2 + FC2 * FC1;
+constexpr int RAW_GRU = RAW_B2 + FC2;
+__host__ __device__ constexpr int gru_in(int l) { return l == 0 ? IN0 : OUT_W; }
+__host__ __device__ constexpr int gru_inp(int l) { return l == 0 ? IN0P : OUT_W; }
+__host__ __device__ constexpr int raw_dir_size(int l) { return G3 * gru_in(l) + G3 * HID + 2 * G3; }
+__host__ __device__ constexpr int raw_gru(int l, int d) {
+    int off = RAW_GRU;
+    for (int i = 0; i < l; ++i) off += 2 * raw_dir_size(i);
+    return off + d * raw_dir_size(l);
+}
+__host__ __device__ constexpr int raw_wih(int l, int d) { return raw_gru(l, d); }
+__host__ __device__ constexpr int raw_whh(int l, int d) { return raw_gru(l, d) + G3 * gru_in(l); }
+__host__ __device__ constexpr int raw_bih(int l, int d) { return raw_whh(l, d) + G3 * HID; }
+__host__ __device__ constexpr int raw_bhh(int l, int d) { return raw_bih(l, d) + G3; }
+constexpr int RAW_W4 = raw_gru(LAYERS, 0);       // (5,256)
+constexpr int RAW_B4 = RAW_W4 + CLASSES * OUT_W;
+constexpr int RAW_TOTAL = RAW_B4 + CLASSES;
+static_assert(RAW_TOTAL == 1099731, "state_dict size (SURVEY.md App. A)");
+
+// ---- packed weights: what the kernels read (fp32, every section 128-byte aligned) ------------
+__host__ __device__ constexpr int align32(int x) { return (x + 31) & ~31; }
+constexpr int W1T_ROWS = READS + 1;              // row 200 is all zero: padding target of the read lists
+constexpr int PK_E = 0;                                          // [c][e]           12 x 50
+constexpr int PK_W1T = align32(PK_E + NCODES * EMB);             // [r][j]          201 x 100
+constexpr int PK_B1 = align32(PK_W1T + W1T_ROWS * FC1);          // [j]
+constexpr int PK_W2 = align32(PK_B1 + FC1);                      // [k][j]           10 x 100
+constexpr int PK_B2 = align32(PK_W2 + FC2 * FC1);                // [k]
+constexpr int PK_GRU = align32(PK_B2 + FC2);
+// per layer:  WIH  [n][k]  n = d*384 + j*3 + g  (gate-interleaved),  k padded to gru_inp(l)
+//             BGI  [n]     b_ih + (g<2 ? b_hh : 0)   (b_hn stays separate: it sits inside r*(.))
+// per (l,d):  WHH  [idx][tid]  the register image of the recurrent kernel (see rec.cu)
+//             BHN  [j]
+constexpr int WHH_REGS = 96;
+constexpr int REC_THREADS = 512;
+__host__ __device__ constexpr int pk_layer_size(int l) {
+    return align32(GI_N * gru_inp(l)) + align32(GI_N) + 2 * (align32(WHH_REGS * REC_THREADS) + align32(HID));
+}
+__host__ __device__ constexpr int pk_layer(int l) {
+    int off = PK_GRU;
+    for (int i = 0; i < l; ++i) off += pk_layer_size(i);
+    return off;
+}
+__host__ __device__ constexpr int pk_wih(int l) { return pk_layer(l); }
+__host__ __device__ constexpr int pk_bgi(int l) { return pk_wih(l) + align32(GI_N * gru_inp(l)); }
+__host__ __device__ constexpr int pk_whh(int l, int d) {
+    return pk_bgi(l) + align32(GI_N) + d * (align32(WHH_REGS * REC_THREADS) + align32(HID));
+}
+__host__ __device__ constexpr int pk_bhn(int l, int d) { return pk_whh(l, d) + align32(WHH_REGS * REC_THREADS); }
+constexpr int PK_W4 = pk_layer(LAYERS);                          // [c][q]            5 x 256
+constexpr int PK_B4 = align32(PK_W4 + CLASSES * OUT_W);
+constexpr int PK_TOTAL = align32(PK_B4 + CLASSES);
+
+// ---- workspace per window (floats) ------------------------------------------------------------
+constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
+constexpr size_t WS_GI = (size_t)COLS * GI_N;    // input projection of one layer, both directions
+constexpr size_t WS_H = (size_t)COLS * OUT_W;    // one layer's output; two buffers ping-pong
+constexpr size_t WS_PER_WINDOW = WS_U + WS_GI + 2 * WS_H;
+
+// small parameters that live in the kernel-parameter constant bank of the front-end kernel
+struct FrontConst {
+    float W2[FC2 * FC1];   // [k][j]
+    float b1[FC1];
+    float b2[FC2];
+};
+
+// ---- launchers (one per translation unit) ------------------------------------------------------
+cudaError_t launch_pack(const float* raw, float* packed, cudaStream_t s);
+cudaError_t launch_narrow_i64(const long long* x64, uint8_t* x8, size_t n, int* status, cudaStream_t s);
+cudaError_t launch_front(const FrontConst& fc, const uint8_t* x, const float* packed, float* u, int nwin,
+                         int* status, int num_sms, cudaStream_t s);
+cudaError_t launch_proj(const float* A, int K, const float* W, const float* bias, float* C, int M,
+                        cudaStream_t s);
+cudaError_t launch_rec(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
+                       float* out, int nwin, int num_sms, cudaStream_t s);
+cudaError_t launch_head(const float* h, const float* w4, const float* b4, float* logits, uint8_t* labels,
+                        int rows, cudaStream_t s);
+cudaError_t measure_fp32_peak(double* tflops);
+cudaError_t front_setup();
+cudaError_t rec_setup();
+
+}  // namespace roko

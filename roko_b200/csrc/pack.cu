@@ -1,0 +1,131 @@
+// Weight packing: raw state_dict order -> the layouts the kernels read.
+// One thread per packed float; runs once per load_state_dict (reference inference.py:95).
+#include "common.cuh"
+
+namespace roko {
+
+__device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) {
+    if (p < PK_W1T) return p < NCODES * EMB ? raw[RAW_E + p] : 0.f;
+    if (p < PK_B1) {                                   // W1T[r][j] = fc1.weight[j][r]; row 200 = 0
+        int i = p - PK_W1T;
+        if (i >= W1T_ROWS * FC1) return 0.f;
+        int r = i / FC1, j = i % FC1;
+        return r < READS ? raw[RAW_W1 + j * READS + r] : 0.f;
+    }
+    if (p < PK_W2) { int i = p - PK_B1; return i < FC1 ? raw[RAW_B1 + i] : 0.f; }
+    if (p < PK_B2) { int i = p - PK_W2; return i < FC2 * FC1 ? raw[RAW_W2 + i] : 0.f; }
+    if (p < PK_GRU) { int i = p - PK_B2; return i < FC2 ? raw[RAW_B2 + i] : 0.f; }
+    if (p < PK_W4) {
+        int l = 0;
+        while (l + 1 < LAYERS && p >= pk_layer(l + 1)) ++l;
+        const int kin = gru_in(l), kp = gru_inp(l);
+        if (p < pk_bgi(l)) {                           // WIH[n][k], n = d*384 + j*3 + g
+            int i = p - pk_wih(l);
+            if (i >= GI_N * kp) return 0.f;
+            int n = i / kp, k = i % kp;
+            int d = n / G3, j = (n % G3) / 3, g = (n % G3) % 3;
+            return k < kin ? raw[raw_wih(l, d) + (g * HID + j) * kin + k] : 0.f;
+        }
+        if (p < pk_whh(l, 0)) {                        // BGI[n] = b_ih + (r,z: b_hh)
+            int n = p - pk_bgi(l);
+            if (n >= GI_N) return 0.f;
+            int d = n / G3, j = (n % G3) / 3, g = (n % G3) % 3;
+            float v = raw[raw_bih(l, d) + g * HID + j];
+            if (g < 2) v += raw[raw_bhh(l, d) + g * HID + j];
+            return v;
+        }
+        int d = p >= pk_whh(l, 1) ? 1 : 0;
+        if (p < pk_bhn(l, d)) {                        // WHH register image [idx][tid]
+            int i = p - pk_whh(l, d);
+            if (i >= WHH_REGS * REC_THREADS) return 0.f;
+            int idx = i / REC_THREADS, tid = i % REC_THREADS;
+            int j = tid >> 2, kq = tid & 3;
+            int g = idx / 32, rem = idx % 32, ii = rem / 4, q = rem % 4;
+            int k = 16 * ii + 4 * kq + q;
+            return raw[raw_whh(l, d) + (g * HID + j) * HID + k];
+        }
+        int j = p - pk_bhn(l, d);
+        return j < HID ? raw[raw_bhh(l, d) + 2 * HID + j] : 0.f;
+    }
+    if (p < PK_B4) { int i = p - PK_W4; return i < CLASSES * OUT_W ? raw[RAW_W4 + i] : 0.f; }
+    { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
+}
+
+__global__ void pack_kernel(const float* __restrict__ raw, float* __restrict__ packed) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < PK_TOTAL) packed[p] = pack_one(raw, p);
+}
+
+// int64 codes (what the reference caller passes, inference.py:113) -> uint8; flags codes > 11
+__global__ void narrow_i64_kernel(const long long* __restrict__ x64, uint8_t* __restrict__ x8, size_t n,
+                                  int* __restrict__ status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) {
+        long long v = x64[i];
+        bad |= (v < 0 || v >= NCODES);
+        x8[i] = (uint8_t)(v < 0 || v > 255 ? 255 : v);
+    }
+    if (bad) atomicOr(status, 1);
+}
+
+// FP32 FFMA peak: 16 independent accumulator chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* sink, float a, float b, int iters) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+cudaError_t measure_fp32_peak(double* tflops) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    float* sink = nullptr;
+    e = cudaMalloc(&sink, sizeof(float));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    const int iters = 1 << 14, blocks = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(t0);
+        ffma_peak_kernel<<<blocks, 256>>>(sink, 0.999f, 0.001f, iters);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        double tf = 2.0 * 16.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(sink);
+    *tflops = best;
+    return e;
+}
+
+cudaError_t launch_pack(const float* raw, float* packed, cudaStream_t s) {
+    pack_kernel<<<(PK_TOTAL + 255) / 256, 256, 0, s>>>(raw, packed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_i64(const long long* x64, uint8_t* x8, size_t n, int* status, cudaStream_t s) {
+    int blocks = (int)((n + 1023) / 1024);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    narrow_i64_kernel<<<blocks, 256, 0, s>>>(x64, x8, n, status);
+    return cudaGetLastError();
+}
+
+}  // namespace roko

@@ -1,0 +1,213 @@
+"""Drop-in for the reference's ``roko/rnn_model.py``: same public names, same constructor,
+same 31 parameter names/shapes (so ``.pth`` files interchange), but ``forward`` runs the
+hand-written sm_100a kernels of ``libroko_b200.so`` through its C ABI instead of torch ops.
+
+Reference interface mirrored here (file:line in /root/reference):
+  * constants ``IN_SIZE, HIDDEN_SIZE, NUM_LAYERS``                     roko/rnn_model.py:10-12
+  * ``gru_init``  (orthogonal matrices, N(0,1) biases)                 roko/rnn_model.py:15-21
+  * ``RNN(in_size, hidden_size, num_layers, dropout=0.2)``             roko/rnn_model.py:24-44
+  * ``RNN.forward(x) -> (B, 90, 5)`` fp32 logits                        roko/rnn_model.py:46-59
+  * callers do ``from rnn_model import *`` and use ``nn`` / ``F``       roko/inference.py:9, train.py:10
+
+Additions (not in the reference): ``predict`` (fused argmax, uint8 labels), ``predict_host``
+(pipelined host-buffer loop), ``forward_taps`` (stage outputs for parity tests).
+
+There is no CPU path: a CPU tensor, a missing library or a non-sm_100 device raise.
+"""
+import ctypes
+import math  # noqa: F401  (re-exported: the reference's callers star-import this module)
+
+import numpy as np  # noqa: F401
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401
+import torch.nn.init as init
+
+from . import _cabi
+
+IN_SIZE = 500
+HIDDEN_SIZE = 128
+NUM_LAYERS = 3
+
+READS, COLS, CLASSES = 200, 90, 5
+MAX_CHUNK = 1024          # windows per internal chunk (bounds scratch: 0.66 MB / window)
+
+
+def gru_init(gru):
+    """Initialisation the reference applies to its GRU (roko/rnn_model.py:15-21)."""
+    for p in gru.parameters():
+        if p.dim() >= 2:
+            init.orthogonal_(p.data)
+        else:
+            init.normal_(p.data)
+
+
+def state_keys():
+    keys = ["embedding.weight", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    for layer in range(NUM_LAYERS):
+        for sfx in ("", "_reverse"):
+            keys += [f"gru.{kind}_l{layer}{sfx}" for kind in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    return keys + ["fc4.weight", "fc4.bias"]
+
+
+class _Handle:
+    """Owns one roko_b200_model (packed weights on one device)."""
+
+    def __init__(self, device_index):
+        self.lib = _cabi.lib()
+        self.ptr = _cabi.c_model_p()
+        _cabi.check(self.lib.roko_b200_model_create(ctypes.byref(self.ptr), device_index))
+        self.device_index = device_index
+        self.version = None
+        self.workspaces = {}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.roko_b200_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class RNN(nn.Module):
+    def __init__(self, in_size, hidden_size, num_layers, dropout=0.2):
+        super().__init__()
+        if (in_size, hidden_size, num_layers) != (IN_SIZE, HIDDEN_SIZE, NUM_LAYERS):
+            raise ValueError("roko_b200 kernels are specialised for RNN(500, 128, 3) "
+                             f"(roko/rnn_model.py:10-12); got {(in_size, hidden_size, num_layers)}")
+        # construction order matches the reference so a given torch seed yields the same weights
+        self.embedding = nn.Embedding(12, 50)
+        self.do = nn.Dropout(dropout)
+        self.fc1 = nn.Linear(READS, 100)
+        self.do1 = nn.Dropout(dropout)
+        self.fc2 = nn.Linear(100, 10)
+        self.do2 = nn.Dropout(dropout)
+        self.hidden_size = hidden_size
+        self.num_layers = num_layers
+        self.gru = nn.GRU(in_size, hidden_size, num_layers=num_layers, batch_first=True,
+                          bidirectional=True, dropout=dropout)
+        gru_init(self.gru)
+        self.fc4 = nn.Linear(2 * hidden_size, CLASSES)
+        self._handles = {}
+
+    # ---- packed-weight cache ------------------------------------------------------------------
+    def _ordered_params(self):
+        sd = dict(self.named_parameters())
+        return [sd[k] for k in state_keys()]
+
+    def _handle(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("roko_b200.RNN runs on CUDA (sm_100a) only; there is no CPU fallback. "
+                               "Move the module and the input to a B200: model.to('cuda')")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            h = self._handles[idx] = _Handle(idx)
+        params = self._ordered_params()
+        for p in params:
+            if p.device.type != "cuda" or (p.device.index or 0) != idx:
+                raise RuntimeError(f"parameter on {p.device}, input on cuda:{idx}")
+        version = tuple((p.data_ptr(), p._version) for p in params)
+        if h.version != version:
+            with torch.no_grad():
+                raw = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params]).contiguous()
+            assert raw.numel() == h.lib.roko_b200_raw_weight_count()
+            stream = torch.cuda.current_stream(idx).cuda_stream
+            _cabi.check(h.lib.roko_b200_model_load(h.ptr, raw.data_ptr(), 1, stream))
+            h.version = version
+        return h
+
+    @staticmethod
+    def _workspace(h, n, idx, stream):
+        need = h.lib.roko_b200_workspace_bytes(min(n, MAX_CHUNK))
+        ws = h.workspaces.get(stream)
+        if ws is None or ws.numel() < need:
+            ws = h.workspaces[stream] = torch.empty(need, dtype=torch.uint8, device=f"cuda:{idx}")
+        return ws
+
+    @staticmethod
+    def _check_input(x):
+        if x.dim() != 3 or x.shape[1] != READS or x.shape[2] != COLS:
+            raise RuntimeError(f"expected input of shape (B, {READS}, {COLS}), got {tuple(x.shape)}")
+        if x.dtype not in (torch.uint8, torch.int64):
+            raise RuntimeError(f"expected uint8 or int64 codes, got {x.dtype}")
+        return x.contiguous()
+
+    def _run(self, x, want_logits, want_labels):
+        x = self._check_input(x)
+        h = self._handle(x.device)
+        idx = h.device_index
+        n = x.shape[0]
+        logits = torch.empty((n, COLS, CLASSES), dtype=torch.float32, device=x.device) if want_logits else None
+        labels = torch.empty((n, COLS), dtype=torch.uint8, device=x.device) if want_labels else None
+        if n == 0:
+            return logits, labels
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        ws = self._workspace(h, n, idx, stream)
+        fn = h.lib.roko_b200_forward_u8 if x.dtype == torch.uint8 else h.lib.roko_b200_forward_i64
+        _cabi.check(fn(h.ptr, x.data_ptr(), n, logits.data_ptr() if want_logits else None,
+                       labels.data_ptr() if want_labels else None, ws.data_ptr(), ws.numel(), stream))
+        return logits, labels
+
+    # ---- reference interface ------------------------------------------------------------------
+    def forward(self, x):
+        """``(B,200,90)`` uint8|int64 codes 0..11 on a CUDA device -> ``(B,90,5)`` fp32 logits."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "roko_b200.RNN implements the inference path (eval mode / no_grad); the training "
+                "forward with dropout and autograd (roko/train.py:46-53) is not built yet")
+        return self._run(x, True, False)[0]
+
+    # ---- additions ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def predict(self, x, return_logits=False):
+        """Fused ``argmax(model(x), 2)`` (roko/inference.py:115-116): uint8 labels ``(B,90)``."""
+        logits, labels = self._run(x, return_logits, True)
+        return (labels, logits) if return_logits else labels
+
+    @torch.no_grad()
+    def predict_host(self, x_host, batch=128, out=None, logits_out=None, device=None):
+        """The loop body of roko/inference.py:111-117 over HOST windows.
+
+        ``x_host``: CPU uint8 tensor ``(N,200,90)`` (pinned memory makes the copies async).
+        Returns CPU uint8 labels ``(N,90)``; copies in/out are inside the call.
+        """
+        if x_host.device.type != "cpu" or x_host.dtype != torch.uint8:
+            raise RuntimeError("predict_host expects a CPU uint8 tensor")
+        x_host = self._check_input(x_host)
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        h = self._handle(dev)
+        n = x_host.shape[0]
+        if out is None:
+            out = torch.empty((n, COLS), dtype=torch.uint8, pin_memory=True)
+        _cabi.check(h.lib.roko_b200_infer_host(h.ptr, x_host.data_ptr(), n, int(batch), out.data_ptr(),
+                                               logits_out.data_ptr() if logits_out is not None else None))
+        return out
+
+    @torch.no_grad()
+    def forward_taps(self, x):
+        """Stage outputs for parity tests: dict(front, gru_l0..2, logits, labels)."""
+        x = self._check_input(x)
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        h = self._handle(x.device)
+        idx, n = h.device_index, x.shape[0]
+        f32 = dict(dtype=torch.float32, device=x.device)
+        t = {"front": torch.empty((n, COLS, IN_SIZE), **f32), "logits": torch.empty((n, COLS, CLASSES), **f32),
+             "labels": torch.empty((n, COLS), dtype=torch.uint8, device=x.device)}
+        for layer in range(NUM_LAYERS):
+            t[f"gru_l{layer}"] = torch.empty((n, COLS, 2 * HIDDEN_SIZE), **f32)
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        need = h.lib.roko_b200_workspace_bytes(n)
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        _cabi.check(h.lib.roko_b200_forward_taps(
+            h.ptr, x.data_ptr(), n, t["front"].data_ptr(), t["gru_l0"].data_ptr(), t["gru_l1"].data_ptr(),
+            t["gru_l2"].data_ptr(), t["logits"].data_ptr(), t["labels"].data_ptr(), ws.data_ptr(), ws.numel(), stream))
+        torch.cuda.current_stream(idx).synchronize()
+        return t
+
+    def check_codes(self):
+        """Synchronise and raise IndexError if an earlier forward saw a code outside 0..11."""
+        for h in self._handles.values():
+            _cabi.check(h.lib.roko_b200_model_check(h.ptr))

@@ -1,0 +1,52 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def seed1_state():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "rand_seed1.pth"), map_location="cpu")
+
+
+@pytest.fixture(scope="session")
+def seed1_weights(seed1_state):
+    return {k: v.numpy() for k, v in seed1_state.items()}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "golden_seed1.npz")))
+
+
+@pytest.fixture(scope="session")
+def edge():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "edge_seed1.npz")))
+
+
+@pytest.fixture(scope="session")
+def cuda_model(seed1_state):
+    """The product path: roko_b200.RNN on cuda:0 with the golden weights (fails loudly w/o GPU/.so)."""
+    import torch
+    from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+    m = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
+    m.load_state_dict(seed1_state, strict=True)
+    return m.to("cuda:0").eval()

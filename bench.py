@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- roko hot-path throughput on B200 (driver contract in the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 128]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path (front end -> 3 x (projection, recurrence) -> head+argmax) over
+one batch of synthetic windows.  Workload at N=1: BASELINE.json configs[1] -- the 128-window batch of
+``inference.py --b 128`` on synthetic (200 reads x 90 columns) uint8 windows with random-init weights
+(the reference-generated ``tests/golden/rand_seed1.pth``).  BASELINE.json's "200 pos x 30 reads" is
+not executable by the reference; the geometry here is the reference's.
+
+Prints ONE JSON line (rank 0).  ``value`` = windows/s with inputs resident in HBM, device-timed;
+``e2e`` = the same metric through ``RNN.predict_host`` (C ABI ``roko_b200_infer_host``) with pinned
+HOST buffers, copies inside the timed region.  ``--impl reference`` times the reference's CPU
+operator sequence (oracle/torch_port.py) on this box's host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+READS, COLS, CLASSES = 200, 90, 5
+WIN_BYTES = READS * COLS
+STAGES = ["front", "proj0", "rec0", "proj1", "rec1", "proj2", "rec2", "head"]
+KERNEL_OF = {"front": "front_kernel", "proj0": "proj_kernel<512>", "proj1": "proj_kernel<256>",
+             "proj2": "proj_kernel<256>", "rec0": "rec_kernel", "rec1": "rec_kernel", "rec2": "rec_kernel",
+             "head": "head_kernel"}
+# algorithmic FLOPs per window (fc1 one-hot factorised)
+FLOPS = {"front": 90 * (200 * 100 + 2 * 100 * 50 * 12) + 2 * 90 * 50 * 100 * 10,
+         "proj0": 2 * 90 * 768 * 500, "proj1": 2 * 90 * 768 * 256, "proj2": 2 * 90 * 768 * 256,
+         "rec0": 2 * 90 * 768 * 128, "rec1": 2 * 90 * 768 * 128, "rec2": 2 * 90 * 768 * 128,
+         "head": 2 * 90 * 256 * 5}
+FLOPS_PER_WINDOW = sum(FLOPS.values())             # 214 813 440
+ALG_BYTES_PER_WINDOW = READS * COLS + COLS         # 18 090: uint8 features in + uint8 labels out
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), world
+
+
+def cpu_reference_run(n_batches, batch, warm_batches, threads=None):
+    """Time the reference's CPU operator sequence on host cores; returns (windows/s, cores, sample)."""
+    import torch
+    from oracle.torch_port import TorchCpuPort
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"), map_location="cpu")
+    threads = threads or os.cpu_count() or 1
+    port = TorchCpuPort(sd, threads=threads)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, 12, (batch, READS, COLS), dtype=torch.uint8, generator=g)
+    for _ in range(warm_batches):
+        port.predict(x)
+    t0 = time.perf_counter()
+    for _ in range(n_batches):
+        port.predict(x)
+    dt = time.perf_counter() - t0
+    return n_batches * batch / dt, torch.get_num_threads(), dt
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    batch = args.batch
+    steps, warm = args.steps, max(1, min(args.warmup, 3))
+    # keep the whole run within a few minutes: shrink the per-step sample when K is large
+    sample = batch if steps <= 100 else max(8, (100 * batch) // steps)
+    wps, cores, dt = cpu_reference_run(steps, sample, warm)
+    line = {
+        "impl": "reference", "metric": "consensus_windows_per_sec", "value": wps, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[0]: reference CPU path, batch={batch}, windows (200 reads x 90 cols) uint8, "
+                               "random-init .pth (tests/golden/rand_seed1.pth)", "batch": batch,
+                   "sample_windows_per_step": sample},
+        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {sample} windows through the reference's stock-torch CPU operator "
+                                   "sequence (oracle/torch_port.py; /root/reference is absent on the GPU box)"},
+        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from roko_b200 import _cabi
+    from roko_b200 import dist as rdist
+    from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a B200: the hot path is CUDA only, there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch, K, W, NS = args.batch, args.steps, max(3, args.warmup), args.streams
+    peaks = load_peaks()
+
+    # ---- model: rank 0 loads the .pth, NCCL-broadcasts the weights ---------------------------------
+    model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
+    if rank == 0:
+        model.load_state_dict(torch.load(os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"), map_location="cpu"))
+    model = model.to(dev).eval()
+    bcast_bytes = rdist.broadcast_weights(model, src=0) if world > 1 else 0
+
+    # ---- parity gate before any timing: golden vectors must come out bit-exact ---------------------
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_seed1.npz"))
+    with torch.no_grad():
+        lab, logit = model.predict(torch.from_numpy(gold["x"]).to(dev), return_logits=True)
+    perr = float(np.abs(logit.cpu().numpy() - gold["logits"]).max())
+    if perr > 1e-4 or not np.array_equal(lab.cpu().numpy(), gold["labels"]):
+        raise SystemExit(f"parity gate failed on rank {rank}: max logit err {perr}")
+
+    # ---- synthetic pool, larger than L2 so no step re-reads its input from cache -------------------
+    P = args.pool_batches
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = torch.randint(0, 12, (P, batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)
+    labels_all = torch.empty((K, batch, COLS), dtype=torch.uint8, device=dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    main = torch.cuda.current_stream(dev)
+
+    def run_steps(n, out):
+        for s in streams:
+            s.wait_stream(main)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % NS]):
+                model.predict(pool[i % P], out=out[i % out.shape[0]])
+        for s in streams:
+            main.wait_stream(s)
+
+    with torch.no_grad():
+        run_steps(W, labels_all)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        run_steps(K, labels_all)
+        gathered = rdist.gather_labels(labels_all.view(K * batch, COLS), K * batch * world) if world > 1 else None
+        e1.record(main)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if rank == 0:
+            assert gathered is not None and gathered.shape == (K * batch * world, COLS)
+    value = K * batch * world / (ms * 1e-3)
+
+    # ---- e2e: pinned host windows -> labels on the host, through the public API ---------------------
+    Ph = min(K, P)
+    x_host = torch.empty((Ph * batch, READS, COLS), dtype=torch.uint8).pin_memory()
+    x_host.copy_(pool[:Ph].view(Ph * batch, READS, COLS))
+    y_host = torch.empty((Ph * batch, COLS), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    model.predict_host(x_host[:3 * batch], batch=batch, out=y_host[:3 * batch])          # warm the slots
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < K:
+        nb = min(Ph, K - done)
+        model.predict_host(x_host[:nb * batch], batch=batch, out=y_host[:nb * batch])
+        done += nb
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = K * batch * world / e2e_s
+
+    # ---- per-kernel device times (CUDA events between the kernels of the chain) -> roofline --------
+    h = model._handle(dev)
+    lib = h.lib
+    ws = torch.empty(lib.roko_b200_workspace_bytes(batch), dtype=torch.uint8, device=dev)
+    st = (ctypes.c_float * 8)()
+    _cabi.check(lib.roko_b200_forward_timed(h.ptr, pool[0].data_ptr(), batch, labels_all[0].data_ptr(), ws.data_ptr(),
+                                             ws.numel(), main.cuda_stream, 20, st))
+    stage_ms = dict(zip(STAGES, [float(v) for v in st]))
+    kern_ms = {}
+    for sname, v in stage_ms.items():
+        kern_ms.setdefault(KERNEL_OF[sname], []).append((sname, v))
+    dom_kernel = max(kern_ms, key=lambda k: sum(v for _, v in kern_ms[k]))
+    dom_stage = max(kern_ms[dom_kernel], key=lambda sv: sv[1])[0]
+    dom_launch_ms = statistics.mean(v for _, v in kern_ms[dom_kernel])
+    dom_flops = statistics.mean(FLOPS[s] for s, _ in kern_ms[dom_kernel]) * batch
+    achieved_tf = dom_flops / (dom_launch_ms * 1e-3) / 1e12
+    fp32 = ctypes.c_double()
+    _cabi.check(lib.roko_b200_measure_fp32_peak(local_rank, ctypes.byref(fp32)))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{dom_kernel}@B{batch}")
+    except Exception:
+        pass
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": "consensus_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"BASELINE configs[1]: batch={batch} synthetic windows (200 reads x 90 cols, uint8 codes 0..11) "
+                            "per step on each GPU, random-init weights tests/golden/rand_seed1.pth, labels out (uint8)",
+                "batch": batch, "windows_per_step_all_gpus": batch * world, "parallelism": f"dp{world}",
+                "streams": NS, "l2": f"inputs cycle through a {P * batch * WIN_BYTES / 1e6:.0f} MB pool (> 126 MB L2)",
+                "collectives": "ncclBroadcast weights %d B before timing; label all-gather inside the timed region" % bcast_bytes
+                               if world > 1 else "none (1 GPU)",
+            },
+            "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": batch * WIN_BYTES,
+                    "d2h_bytes_per_step": batch * COLS, "api": "RNN.predict_host -> roko_b200_infer_host (pinned host buffers)"},
+            "gpu_launches": K * 8,
+            "clocks": clocks,
+            "parity": {"golden_max_abs_logit_err": perr, "golden_labels_exact": True},
+            "roofline": {"bound": "tensor", "kernel": dom_kernel, "stage": dom_stage, "achieved": achieved_tf,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                         "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside the step)",
+                         "note": "fp32-exact path on the FFMA pipe; fraction of the measured fp32 FFMA peak is in fp32_frac"},
+            "fp32": {"peak_tflops_measured": fp32.value, "kernel_frac": achieved_tf / fp32.value if fp32.value else None,
+                     "path_tflops": value / world * FLOPS_PER_WINDOW / 1e12,
+                     "path_frac": value / world * FLOPS_PER_WINDOW / 1e12 / fp32.value if fp32.value else None},
+            "hbm": {"algorithmic_bytes_per_window": ALG_BYTES_PER_WINDOW, "achieved_gbs": value / world * ALG_BYTES_PER_WINDOW / 1e9,
+                    "peak_gbs": peaks["hbm_gbs"], "frac": value / world * ALG_BYTES_PER_WINDOW / 1e9 / peaks["hbm_gbs"],
+                    "note": "path is compute/latency bound (AI ~ 12 kFLOP/B); HBM fraction is <1 % by construction"},
+            "stage_ms": stage_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            wps, cores, dt = cpu_reference_run(8, 128, 2)
+            line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+                                    "sample": f"1024 windows (8 x 128) in {dt:.1f} s through the reference's stock-torch CPU "
+                                              "operator sequence (oracle/torch_port.py)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--pool-batches", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,13 +134,19 @@ class RNN(nn.Module):
             raise RuntimeError(f"expected uint8 or int64 codes, got {x.dtype}")
         return x.contiguous()
 
-    def _run(self, x, want_logits, want_labels):
+    def _run(self, x, want_logits, want_labels, labels_out=None):
         x = self._check_input(x)
         h = self._handle(x.device)
         idx = h.device_index
         n = x.shape[0]
         logits = torch.empty((n, COLS, CLASSES), dtype=torch.float32, device=x.device) if want_logits else None
-        labels = torch.empty((n, COLS), dtype=torch.uint8, device=x.device) if want_labels else None
+        labels = None
+        if want_labels:
+            labels = labels_out if labels_out is not None else \
+                torch.empty((n, COLS), dtype=torch.uint8, device=x.device)
+            if (labels.dtype != torch.uint8 or tuple(labels.shape) != (n, COLS) or not labels.is_contiguous()
+                    or labels.device != x.device):
+                raise RuntimeError("labels_out must be a contiguous uint8 (B, 90) tensor on the input's device")
         if n == 0:
             return logits, labels
         stream = torch.cuda.current_stream(idx).cuda_stream
@@ -161,9 +167,9 @@ class RNN(nn.Module):
 
     # ---- additions ----------------------------------------------------------------------------
     @torch.no_grad()
-    def predict(self, x, return_logits=False):
+    def predict(self, x, return_logits=False, out=None):
         """Fused ``argmax(model(x), 2)`` (roko/inference.py:115-116): uint8 labels ``(B,90)``."""
-        logits, labels = self._run(x, return_logits, True)
+        logits, labels = self._run(x, return_logits, True, out)
         return (labels, logits) if return_logits else labels
 
     @torch.no_grad()

@@ -32,8 +32,8 @@ if ROOT not in sys.path:
 READS, COLS, CLASSES = 200, 90, 5
 WIN_BYTES = READS * COLS
 STAGES = ["front", "proj0", "rec0", "proj1", "rec1", "proj2", "rec2", "head"]
-KERNEL_OF = {"front": "front_kernel", "proj0": "proj_kernel<512>", "proj1": "proj_kernel<256>",
-             "proj2": "proj_kernel<256>", "rec0": "rec_kernel", "rec1": "rec_kernel", "rec2": "rec_kernel",
+KERNEL_OF = {"front": "front_kernel", "proj0": "proj_tc_kernel<512>", "proj1": "proj_tc_kernel<256>",
+             "proj2": "proj_tc_kernel<256>", "rec0": "rec_kernel", "rec1": "rec_kernel", "rec2": "rec_kernel",
              "head": "head_kernel"}
 # algorithmic FLOPs per window (fc1 one-hot factorised)
 FLOPS = {"front": 90 * (200 * 100 + 2 * 100 * 50 * 12) + 2 * 90 * 50 * 100 * 10,

@@ -1,6 +1,7 @@
 // C ABI of libroko_b200 (include/roko_b200.h): model lifetime, weight packing, the forward pass
 // as a chain of kernels on the caller's stream, and the pipelined host-buffer loop.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -48,6 +49,7 @@ struct roko_b200_model {
     float* raw_stage = nullptr;
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
+    bool use_tc = true;             // tcgen05 3xTF32 projection (ROKO_B200_PROJ=ffma selects the FFMA SGEMM)
     FrontConst fc;
     struct Slot {
         cudaStream_t stream = nullptr;
@@ -91,7 +93,10 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
         float* outs[3] = {h0, h1, h0};
         for (int l = 0; l < LAYERS; ++l) {
             if (ev) CU(cudaEventRecord(ev[1 + 2 * l], s));
-            CU(launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s));
+            if (m->use_tc)
+                CU(launch_proj_tc(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, s));
+            else
+                CU(launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s));
             if (ev) CU(cudaEventRecord(ev[2 + 2 * l], s));
             CU(launch_rec(gi, pk + pk_whh(l, 0), dstride, pk + pk_bhn(l, 0), outs[l], nc, m->num_sms, s));
             if (taps && taps->gru[l])
@@ -168,6 +173,11 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
     if (e == cudaSuccess) e = front_setup();
     if (e == cudaSuccess) e = rec_setup();
+    if (e == cudaSuccess) e = proj_tc_setup();
+    {
+        const char* pj = getenv("ROKO_B200_PROJ");
+        m->use_tc = !(pj && strcmp(pj, "ffma") == 0);
+    }
     if (e != cudaSuccess) {
         roko_b200_model_destroy(m);
         return fail(ROKO_B200_ECUDA, "model_create: %s%s", cudaGetErrorString(e));

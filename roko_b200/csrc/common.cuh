@@ -81,7 +81,17 @@ __host__ __device__ constexpr int pk_whh(int l, int d) {
 __host__ __device__ constexpr int pk_bhn(int l, int d) { return pk_whh(l, d) + align32(WHH_REGS * REC_THREADS); }
 constexpr int PK_W4 = pk_layer(LAYERS);                          // [c][q]            5 x 256
 constexpr int PK_B4 = align32(PK_W4 + CLASSES * OUT_W);
-constexpr int PK_TOTAL = align32(PK_B4 + CLASSES);
+// tensor-core projection weights: W_ih split into tf32 hi/lo and stored as ready-to-copy shared-memory
+// images (K-major, 128-byte swizzle) -- see proj_tc.cu.  [n_tile][k_block][hi|lo][256 rows x 32 floats]
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32;
+constexpr int TC_IMG = TC_BN * TC_BK;            // floats in one hi (or lo) image: 32 KB
+__host__ __device__ constexpr int pk_wtc_size(int l) { return (GI_N / TC_BN) * (gru_inp(l) / TC_BK) * 2 * TC_IMG; }
+__host__ __device__ constexpr int pk_wtc(int l) {
+    int off = align32(PK_B4 + CLASSES);
+    for (int i = 0; i < l; ++i) off += pk_wtc_size(i);
+    return off;
+}
+constexpr int PK_TOTAL = pk_wtc(LAYERS);
 
 // ---- workspace per window (floats) ------------------------------------------------------------
 constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
@@ -103,6 +113,9 @@ cudaError_t launch_front(const FrontConst& fc, const uint8_t* x, const float* pa
                          int* status, int num_sms, cudaStream_t s);
 cudaError_t launch_proj(const float* A, int K, const float* W, const float* bias, float* C, int M,
                         cudaStream_t s);
+cudaError_t launch_proj_tc(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
+                           cudaStream_t s);
+cudaError_t proj_tc_setup();
 cudaError_t launch_rec(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
                        float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t launch_head(const float* h, const float* w4, const float* b4, float* logits, uint8_t* labels,

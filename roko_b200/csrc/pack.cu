@@ -48,7 +48,31 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) 
         return j < HID ? raw[raw_bhh(l, d) + 2 * HID + j] : 0.f;
     }
     if (p < PK_B4) { int i = p - PK_W4; return i < CLASSES * OUT_W ? raw[RAW_W4 + i] : 0.f; }
-    { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
+    if (p < pk_wtc(0)) { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
+    {   // tf32 hi/lo images of W_ih in the swizzled shared-memory layout of proj_tc.cu
+        int l = 0;
+        while (l + 1 < LAYERS && p >= pk_wtc(l + 1)) ++l;
+        const int kin = gru_in(l), kblocks = gru_inp(l) / TC_BK;
+        int i = p - pk_wtc(l);
+        const int ntile = i / (kblocks * 2 * TC_IMG);
+        i %= kblocks * 2 * TC_IMG;
+        const int kb = i / (2 * TC_IMG);
+        i %= 2 * TC_IMG;
+        const int half = i / TC_IMG;
+        const int ob = (i % TC_IMG) * 4;                 // byte offset inside the 32 KB image
+        const int rgrp = ob / 1024, within = ob % 1024;
+        const int r8 = within / 128, pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+        const int r = rgrp * 8 + r8;
+        const int kk = ((pchunk ^ r8) * 4) + w4;         // undo the 128B swizzle: logical 16B chunk
+        const int k = kb * TC_BK + kk;
+        const int n = ntile * TC_BN + r;
+        const int d = n / G3, j = (n % G3) / 3, g = (n % G3) % 3;
+        const float v = k < kin ? raw[raw_wih(l, d) + (g * HID + j) * kin + k] : 0.f;
+        unsigned hi_bits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi_bits) : "f"(v));
+        const float hi = __uint_as_float(hi_bits);
+        return half == 0 ? hi : v - hi;
+    }
 }
 
 __global__ void pack_kernel(const float* __restrict__ raw, float* __restrict__ packed) {

@@ -12,13 +12,35 @@
 // over the 4 kq lanes finishes the dot products.  Lane kq then owns window kq of the group: gate
 // math, h kept in a register, new h to shared (double buffered -> one barrier per step) and to
 // the layer output.  gi for step s+1 is prefetched while step s computes.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace roko {
 
 constexpr int HS_STRIDE = HID + 8;     // +8 floats: the 4 kq lanes' h stores land in distinct banks
 
-__device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+// sigmoid / tanh on the MUFU pipe: ex2.approx (<= 2 ulp) + rcp.approx (<= 1 ulp); absolute error
+// ~3e-7, the size of fp32 rounding noise in the reference's own CPU evaluation.
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+#ifdef ROKO_ACCURATE_GATES
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ float tanh_f(float v) { return tanhf(v); }
+#else
+__device__ __forceinline__ float sigmoid_f(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float tanh_f(float v) {
+    return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * v)), -1.f);
+}
+#endif
 
 template <int NB>
 __global__ void __launch_bounds__(REC_THREADS, 1)
@@ -39,26 +61,23 @@ rec_kernel(const float* __restrict__ gi, const float* __restrict__ whh0, size_t 
     for (int grp = blockIdx.x >> 1; grp < ngroups; grp += gridDim.x >> 1) {
         const int b0 = grp * NB;
         const bool mine = kq < NB && (b0 + kq) < nwin;      // this lane finishes window b0+kq
-        const size_t row0 = (size_t)(b0 + (mine ? kq : 0)) * COLS;
-        const float* gp = gi + row0 * GI_N + dir * G3 + j * 3;
-        float* op = out + row0 * OUT_W + dir * HID + j;
+        const int row0 = (b0 + (mine ? kq : 0)) * COLS;
+        int t = dir ? COLS - 1 : 0;
+        const int dt = dir ? -1 : 1;
+        // 32-bit element offsets (a chunk is far below 2^31 floats): fewer live registers
+        unsigned gofs = (unsigned)(row0 + t) * GI_N + dir * G3 + j * 3;
+        unsigned oofs = (unsigned)(row0 + t) * OUT_W + dir * HID + j;
+        const int gstep = dt * GI_N, ostep = dt * OUT_W;
 
         __syncthreads();                                     // previous group's readers are done
         for (int i = tid; i < 2 * NB * HS_STRIDE; i += REC_THREADS) (&hs[0][0][0])[i] = 0.f;
         float hprev = 0.f;
-        int t = dir ? COLS - 1 : 0;
-        const int dt = dir ? -1 : 1;
-        float g_r = 0.f, g_z = 0.f, g_n = 0.f;
-        if (mine) { const float* p = gp + (size_t)t * GI_N; g_r = p[0]; g_z = p[1]; g_n = p[2]; }
+        float g_r = 0.f, g_z = 0.f, g_n = 0.f;               // gi of the step about to run
+        if (mine) { g_r = gi[gofs]; g_z = gi[gofs + 1]; g_n = gi[gofs + 2]; }
         __syncthreads();
 
         for (int s = 0; s < COLS; ++s) {
             const int cur = s & 1;
-            float n_r = 0.f, n_z = 0.f, n_n = 0.f;           // prefetch gi of the next step
-            if (mine && s + 1 < COLS) {
-                const float* p = gp + (size_t)(t + dt) * GI_N;
-                n_r = p[0]; n_z = p[1]; n_n = p[2];
-            }
             float acc[NB][3];
 #pragma unroll
             for (int b = 0; b < NB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
@@ -76,43 +95,78 @@ rec_kernel(const float* __restrict__ gi, const float* __restrict__ whh0, size_t 
                     }
                 }
             }
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
+            // finish the dot products over the 4 kq lanes; lane kq ends up with window kq's sums
+            float a_r, a_z, a_n;
+            if (NB == 4) {
+                // reduce-scatter: 9 shuffles instead of a 24-shuffle all-reduce
+                const bool hi1 = kq & 1, hi2 = kq & 2;
+                float k0[3], k1[3];
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                    acc[b][g] += __shfl_xor_sync(0xffffffffu, acc[b][g], 1);
-                    acc[b][g] += __shfl_xor_sync(0xffffffffu, acc[b][g], 2);
+                    // stage 1 (xor 1): keep windows of my parity {kq&1, 2+(kq&1)}, send the others
+                    const float s0 = hi1 ? acc[0][g] : acc[1][g];
+                    const float s1 = hi1 ? acc[2][g] : acc[3][g];
+                    k0[g] = (hi1 ? acc[1][g] : acc[0][g]) + __shfl_xor_sync(0xffffffffu, s0, 1);
+                    k1[g] = (hi1 ? acc[3][g] : acc[2][g]) + __shfl_xor_sync(0xffffffffu, s1, 1);
                 }
-            float a_r = acc[0][0], a_z = acc[0][1], a_n = acc[0][2];
+                // stage 2 (xor 2): keep window kq = (kq&1) + 2*(kq>>1)
+                {
+                    const float sr = hi2 ? k0[0] : k1[0], sz = hi2 ? k0[1] : k1[1], sn = hi2 ? k0[2] : k1[2];
+                    a_r = (hi2 ? k1[0] : k0[0]) + __shfl_xor_sync(0xffffffffu, sr, 2);
+                    a_z = (hi2 ? k1[1] : k0[1]) + __shfl_xor_sync(0xffffffffu, sz, 2);
+                    a_n = (hi2 ? k1[2] : k0[2]) + __shfl_xor_sync(0xffffffffu, sn, 2);
+                }
+            } else {
 #pragma unroll
-            for (int b = 1; b < NB; ++b)
-                if (kq == b) { a_r = acc[b][0]; a_z = acc[b][1]; a_n = acc[b][2]; }
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        acc[b][g] += __shfl_xor_sync(0xffffffffu, acc[b][g], 1);
+                        acc[b][g] += __shfl_xor_sync(0xffffffffu, acc[b][g], 2);
+                    }
+                a_r = acc[0][0]; a_z = acc[0][1]; a_n = acc[0][2];
+                if (NB == 2 && kq == 1) { a_r = acc[NB - 1][0]; a_z = acc[NB - 1][1]; a_n = acc[NB - 1][2]; }
+            }
             if (mine) {
-                const float r = sigmoid_acc(g_r + a_r);
-                const float z = sigmoid_acc(g_z + a_z);
-                const float n = tanhf(g_n + r * (a_n + bhn));
-                const float h = (1.f - z) * n + z * hprev;
+                const float r = sigmoid_f(g_r + a_r);
+                const float z = sigmoid_f(g_z + a_z);
+                const float n = tanh_f(g_n + r * (a_n + bhn));
+                const float h = fmaf(z, hprev - n, n);       // (1 - z) * n + z * h
                 hprev = h;
                 hs[cur ^ 1][kq][j] = h;
-                op[(size_t)t * OUT_W] = h;
+                out[oofs] = h;
+                gofs += gstep; oofs += ostep;
+                if (s + 1 < COLS) { g_r = gi[gofs]; g_z = gi[gofs + 1]; g_n = gi[gofs + 2]; }   // a full step ahead
             }
-            g_r = n_r; g_z = n_z; g_n = n_n;
-            t += dt;
             __syncthreads();
         }
     }
 }
 
-cudaError_t rec_setup() { return cudaSuccess; }
+constexpr double REC_C0 = 600.0, REC_C1 = 450.0;
+static int g_force_nb = 0;
+
+cudaError_t rec_setup() {
+    const char* e = getenv("ROKO_B200_REC_NB");              // tuning / profiling override
+    g_force_nb = e ? atoi(e) : 0;
+    return cudaSuccess;
+}
 
 cudaError_t launch_rec(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
                        float* out, int nwin, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
     // CTAs come in (fwd, bwd) pairs; pick the largest group size that still fills the machine
+    // cost model (cycles per step ~ C0 + C1*nb, measured) x rounds each CTA pair has to run
     const int pairs = num_sms / 2;
     int nb = 1;
-    if (nwin >= 2 * pairs) nb = 2;
-    if (nwin >= 8 * pairs) nb = 4;
+    double best = 1e30;
+    for (int cand = 1; cand <= 4; cand *= 2) {
+        const int groups = (nwin + cand - 1) / cand;
+        const int rounds = (groups + pairs - 1) / pairs;
+        const double cost = rounds * (REC_C0 + REC_C1 * cand);
+        if (cost < best) { best = cost; nb = cand; }
+    }
+    if (g_force_nb == 1 || g_force_nb == 2 || g_force_nb == 4) nb = g_force_nb;
     const int ngroups = (nwin + nb - 1) / nb;
     const int grid = 2 * (ngroups < pairs ? ngroups : pairs);
     if (nb == 1) rec_kernel<1><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin);

@@ -45,7 +45,8 @@ def _compile(src, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     if not _stale(obj, [os.path.join(CSRC, src)] + _deps()):
         return obj, ""
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("ROKO_B200_EXTRA_NVCC", "").split()      # tuning experiments only
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{p.stdout}\n{p.stderr}")

@@ -7,94 +7,130 @@
 //     M[p][j][c] = sum_{r : x[r][p] == c} W1[j][r]                 (adds only)
 //     a[p][e][j] = relu(b1[j] + sum_c M[p][j][c] * E[c][e])
 //     g[p][e][k] = relu(b2[k] + sum_j W2[k][j] * a[p][e][j])
-// One CTA owns a window (18 000 contiguous bytes, staged once in shared memory) and walks its
-// 90 columns in chunks of CC:
-//   phase 1  one warp per column: counting sort of the 200 reads by code -> per-code read lists,
-//            each padded to a multiple of 4 with the index of an all-zero W1T row
-//   phase 2  thread = (column, 4 consecutive j): sums W1T rows over each list (LDS.128 + 4 FADD
-//            per read) -> M in shared memory
-//   phase 3  thread = (column, e): a and g entirely in registers; W2/b1/b2 come from the kernel
-//            parameter constant bank so every FFMA takes its weight operand for free
+//
+// One persistent CTA per SM walks windows.  A window (18 000 contiguous bytes) arrives by a single
+// TMA bulk copy, double buffered so the next window lands while this one computes.  Per window:
+//   sort      all 16 warps: counting sort of each column's 200 reads by code -> per-code read
+//             lists, each padded to a multiple of 4 with the index of an all-zero W1T row
+//   then a warp-specialised pipeline over chunks of 6 columns, double buffered through M:
+//   producers (6 warps) thread = (column, 4 consecutive j): sum W1T rows over each list
+//             (LDS.128 + 4 FADD per read) -> M chunk in shared memory
+//   consumers (10 warps) thread = (column, e): a and g entirely in registers; W2/b1/b2 come from
+//             the kernel-parameter constant bank, M rows are warp-broadcast LDS.128
+// Producers and consumers meet only at named barriers (full/empty per M buffer).
 #include "common.cuh"
 
 namespace roko {
 
 constexpr int FR_THREADS = 512;
-constexpr int CC = 8;             // columns per chunk: phase 3 uses 64 threads per column
-constexpr int LIST_LEN = 240;     // 200 reads + up to 3 pads for each of 12 codes
+constexpr int FR_PROD = 192;                  // producer threads (6 warps)
+constexpr int FR_CONS = FR_THREADS - FR_PROD; // consumer threads (10 warps)
+constexpr int CC = 5;                         // columns per chunk: 125 producer tasks, 5 x 64 consumer threads
+constexpr int NCHUNK = COLS / CC;             // 18
+constexpr int LIST_LEN = 240;                 // 200 reads + up to 3 pads for each of 12 codes
 constexpr int JQ = FC1 / 4;
+static_assert(COLS % CC == 0 && CC * JQ <= FR_PROD && CC * 64 <= FR_CONS, "role sizes");
 
 struct FrontSmem {
-    float w1t[W1T_ROWS * FC1];                 // 80 400 B  [r][j], row 200 zero
-    float ms[CC][FC1][NCODES];                 // 38 400 B
-    alignas(16) uint8_t xs[READS * COLS];      // 18 000 B  the window, [read][col]
-    alignas(16) uint8_t lists[CC][LIST_LEN];
-    int starts[CC][16];
+    float w1t[W1T_ROWS * FC1];                     // 80 400 B  [r][j], row 200 zero
+    float ms[2][CC][FC1][NCODES];                  // 48 000 B  double-buffered M chunk
+    alignas(16) uint8_t xs[2][READS * COLS];      // 36 000 B  double-buffered window, [read][col]
+    alignas(16) uint8_t lists[COLS][LIST_LEN];     // 21 600 B  (240 is a multiple of 8: uint2 loads stay aligned)
+    uint8_t starts[COLS][16];                      //  1 440 B
+    alignas(8) unsigned long long xbar[2];         // TMA arrival barriers of the two window buffers
 };
 
-__device__ __forceinline__ void sort_column(FrontSmem& S, int cl, int p, int lane, int* status) {
-    uint32_t codes[7];
-    int cnt[NCODES];
-#pragma unroll
-    for (int c = 0; c < NCODES; ++c) cnt[c] = 0;
-    bool bad = false;
-#pragma unroll
-    for (int it = 0; it < 7; ++it) {
-        int r = it * 32 + lane;
-        uint32_t code = r < READS ? S.xs[r * COLS + p] : 255u;
-        bad |= (r < READS && code >= NCODES);
-        codes[it] = code;
-#pragma unroll
-        for (int c = 0; c < NCODES; ++c) cnt[c] += __popc(__ballot_sync(0xffffffffu, code == (uint32_t)c));
-    }
-    if (bad) atomicOr(status, 1);              // nn.Embedding would raise IndexError (CPU) / assert (CUDA)
-    int base[NCODES], end[NCODES];
-    int run = 0;
-#pragma unroll
-    for (int c = 0; c < NCODES; ++c) {
-        base[c] = run;
-        if (lane == 0) S.starts[cl][c] = run;
-        run += (cnt[c] + 3) & ~3;
-        end[c] = run;
-    }
-    if (lane == 0) S.starts[cl][NCODES] = run;
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int it = 0; it < 7; ++it) {
-        uint32_t code = codes[it];
-#pragma unroll
-        for (int c = 0; c < NCODES; ++c) {
-            uint32_t m = __ballot_sync(0xffffffffu, code == (uint32_t)c);
-            if (code == (uint32_t)c) S.lists[cl][base[c] + __popc(m & lt)] = (uint8_t)(it * 32 + lane);
-            base[c] += __popc(m);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < NCODES; ++c)
-        if (lane < end[c] - base[c]) S.lists[cl][base[c] + lane] = (uint8_t)READS;   // zero row
+// named barrier ids (0 is __syncthreads)
+constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(FR_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(FR_THREADS) : "memory"); }
+
+__device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Counting sort of one column's 200 reads by code, one warp per column.  Lane l owns the 7
+// consecutive reads 7l..7l+6, keeps a per-code histogram packed as bytes in three 32-bit words
+// (4 codes each; a warp total never exceeds 200 < 256), and a 5-step shuffle scan turns the
+// histograms into write positions.  Reads stay in ascending order inside every code's list.
+__device__ __forceinline__ uint32_t byte_of(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t code) {
+    const uint32_t w = code < 4 ? w0 : (code < 8 ? w1 : w2);
+    return (w >> ((code & 3u) * 8u)) & 0xffu;
 }
 
-__device__ __forceinline__ void build_m(FrontSmem& S, int cl, int jq) {
+__device__ __forceinline__ void sort_column(FrontSmem& S, const uint8_t* xs, int p, int lane, int* status) {
+    uint32_t codes[7];
+    uint32_t h0 = 0, h1 = 0, h2 = 0;               // my histogram
+    uint32_t rank[7];                              // rank of read i among my earlier reads of the same code
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const int r = lane * 7 + i;
+        uint32_t code = r < READS ? xs[r * COLS + p] : 15u;
+        bad |= (r < READS && code >= NCODES);
+        if (code >= NCODES) code = 15u;            // 15 -> no list
+        codes[i] = code;
+        rank[i] = byte_of(h0, h1, h2, code);
+        const uint32_t inc = 1u << ((code & 3u) * 8u);
+        h0 += code < 4 ? inc : 0u;
+        h1 += (code >= 4 && code < 8) ? inc : 0u;
+        h2 += (code >= 8 && code < 12) ? inc : 0u;
+    }
+    if (bad) atomicOr(status, 1);                  // nn.Embedding would raise IndexError (CPU) / assert (CUDA)
+    uint32_t s0 = h0, s1 = h1, s2 = h2;            // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o),
+                       t2 = __shfl_up_sync(0xffffffffu, s2, o);
+        if (lane >= o) { s0 += t0; s1 += t1; s2 += t2; }
+    }
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31),
+                   tot2 = __shfl_sync(0xffffffffu, s2, 31);
+    const uint32_t e0 = s0 - h0, e1 = s1 - h1, e2 = s2 - h2;      // exclusive prefix of my lane
+    // list starts, each list padded to a multiple of 4; packed the same way (start <= 236 fits a byte)
+    uint32_t st0 = 0, st1 = 0, st2 = 0, run = 0;
+#pragma unroll
+    for (int c = 0; c < NCODES; ++c) {
+        const uint32_t cnt = byte_of(tot0, tot1, tot2, c);
+        const uint32_t sh = (c & 3) * 8;
+        if (c < 4) st0 |= run << sh; else if (c < 8) st1 |= run << sh; else st2 |= run << sh;
+        if (lane == 0) S.starts[p][c] = (uint8_t)run;
+        const uint32_t end = run + ((cnt + 3u) & ~3u);
+        if (lane < (int)(end - run - cnt)) S.lists[p][run + cnt + lane] = (uint8_t)READS;   // pad -> zero row
+        run = end;
+    }
+    if (lane == 0) S.starts[p][NCODES] = (uint8_t)run;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const uint32_t code = codes[i];
+        if (code < NCODES) {
+            const uint32_t pos = byte_of(st0, st1, st2, code) + byte_of(e0, e1, e2, code) + rank[i];
+            S.lists[p][pos] = (uint8_t)(lane * 7 + i);
+        }
+    }
+}
+
+__device__ __forceinline__ void build_m(FrontSmem& S, int buf, int cl, int p, int jq) {
     const float4* w4 = reinterpret_cast<const float4*>(S.w1t);
     float4 acc[NCODES];
+    auto add4 = [&](float4& a, uint32_t q) {       // four list entries -> four W1T rows
+        const float4 v0 = w4[(q & 0xffu) * JQ + jq];
+        const float4 v1 = w4[((q >> 8) & 0xffu) * JQ + jq];
+        const float4 v2 = w4[((q >> 16) & 0xffu) * JQ + jq];
+        const float4 v3 = w4[(q >> 24) * JQ + jq];
+        a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+        a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+        a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+        a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
+    };
 #pragma unroll
     for (int c = 0; c < NCODES; ++c) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int i0 = S.starts[cl][c], i1 = S.starts[cl][c + 1];
-        for (int i = i0; i < i1; i += 4) {
-            const uint32_t q = *reinterpret_cast<const uint32_t*>(&S.lists[cl][i]);
-            const float4 v0 = w4[(q & 0xffu) * JQ + jq];
-            const float4 v1 = w4[((q >> 8) & 0xffu) * JQ + jq];
-            const float4 v2 = w4[((q >> 16) & 0xffu) * JQ + jq];
-            const float4 v3 = w4[(q >> 24) * JQ + jq];
-            a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
-            a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
-            a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
-            a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
-        }
+        const int i0 = S.starts[p][c], i1 = S.starts[p][c + 1];
+#pragma unroll 1
+        for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&S.lists[p][i]));
         acc[c] = a;
     }
-    float4* m = reinterpret_cast<float4*>(&S.ms[cl][4 * jq][0]);
+    float4* m = reinterpret_cast<float4*>(&S.ms[buf][cl][4 * jq][0]);
     m[0] = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
     m[1] = make_float4(acc[4].x, acc[5].x, acc[6].x, acc[7].x);
     m[2] = make_float4(acc[8].x, acc[9].x, acc[10].x, acc[11].x);
@@ -115,49 +151,99 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem& S = *reinterpret_cast<FrontSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t WIN_BYTES = READS * COLS;
 
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fr_smem_u32(&S.xbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fr_smem_u32(&S.xbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     {   // W1T (with its zero row) stays resident for every window this CTA processes
         const float4* src = reinterpret_cast<const float4*>(packed + PK_W1T);
         float4* dst = reinterpret_cast<float4*>(S.w1t);
         for (int i = tid; i < W1T_ROWS * FC1 / 4; i += FR_THREADS) dst[i] = src[i];
     }
-    const int cl3 = tid >> 6, e = tid & 63;
+    __syncthreads();
+    auto fetch_window = [&](int w, int buf) {      // one thread: TMA bulk copy of a whole window
+        const uint32_t bar = fr_smem_u32(&S.xbar[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(WIN_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(fr_smem_u32(S.xs[buf])), "l"(x + (size_t)w * WIN_BYTES), "r"(WIN_BYTES), "r"(bar) : "memory");
+    };
+    if (tid == 0 && (int)blockIdx.x < nwin) fetch_window(blockIdx.x, 0);
+
+    // consumer identity: (column within chunk, embedding dim)
+    // Consumers take the LOW warp ids, producers the HIGH ones: the warp arbiter favours high warp
+    // ids, so the latency-bound gather keeps running underneath the FFMA-bound consumers (measured:
+    // with the roles the other way round the two phases serialised, 0.225 ms -> see DESIGN.md).
+    const int ct = tid;
+    const bool is_cons = tid < FR_CONS;
+    const int pt = tid - FR_CONS;                  // producer thread index
+    // two warps per column (lanes 50..52 of the pair zero the k-padding): every M-row LDS.128 is a
+    // pure warp broadcast = one shared-memory wavefront
+    const int ccol = is_cons ? ct >> 6 : 0, e = is_cons ? ct & 63 : 0;
+    const bool cons_active = is_cons && ccol < CC && e < EMB;
+    const int zt = (is_cons && ccol < CC) ? e - EMB : -1;
     float Ee[NCODES];
 #pragma unroll
-    for (int c = 0; c < NCODES; ++c) Ee[c] = e < EMB ? packed[PK_E + c * EMB + e] : 0.f;
+    for (int c = 0; c < NCODES; ++c) Ee[c] = cons_active ? packed[PK_E + c * EMB + e] : 0.f;
 
-    for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
-        __syncthreads();
-        {   // the window: 18 000 contiguous bytes, 16-byte vector loads
-            const int4* src = reinterpret_cast<const int4*>(x + (size_t)w * (READS * COLS));
-            int4* dst = reinterpret_cast<int4*>(S.xs);
-            for (int i = tid; i < READS * COLS / 16; i += FR_THREADS) dst[i] = __ldg(src + i);
+    int it = 0;
+    for (int w = blockIdx.x; w < nwin; w += gridDim.x, ++it) {
+        const int xb = it & 1;
+        {   // wait for this window's bytes
+            const uint32_t bar = fr_smem_u32(&S.xbar[xb]), parity = (it >> 1) & 1;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "W_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra D_%=;\n\t"
+                "bra W_%=;\n\t"
+                "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
         }
-        __syncthreads();
-        for (int p0 = 0; p0 < COLS; p0 += CC) {
-            const int ncol = min(CC, COLS - p0);
-            if (warp < ncol) sort_column(S, warp, p0 + warp, lane, status);
-            __syncthreads();
-            if (tid < ncol * JQ) build_m(S, tid / JQ, tid % JQ);
-            __syncthreads();
-            if (cl3 < ncol) {
-                float* urow = u + ((size_t)w * COLS + p0 + cl3) * IN0P;
-                if (e < EMB) {
+#ifndef FR_SKIP_SORT
+        for (int p = warp; p < COLS; p += FR_THREADS / 32) sort_column(S, S.xs[xb], p, lane, status);
+#endif
+        __syncthreads();                           // lists complete; xs[xb^1] (previous window) is free
+        if (tid == 0 && w + (int)gridDim.x < nwin) fetch_window(w + gridDim.x, xb ^ 1);
+
+        if (!is_cons) {
+            // ---------------------------- producers: M chunks ------------------------------------
+            const int cl = pt / JQ, jq = pt % JQ;
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int buf = ch & 1;
+                if (ch >= 2) bar_sync(BAR_EMPTY + buf);             // consumers released this buffer
+#ifndef FR_SKIP_BUILD
+                if (cl < CC) build_m(S, buf, cl, ch * CC + cl, jq);
+#endif
+                __threadfence_block();
+                bar_arrive(BAR_FULL + buf);
+            }
+        } else {
+            // ---------------------------- consumers: a, g -----------------------------------------
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int buf = ch & 1;
+                bar_sync(BAR_FULL + buf);
+                float* urow = u + ((size_t)w * COLS + ch * CC + (ccol < CC ? ccol : 0)) * IN0P;
+#ifdef FR_SKIP_CONS
+                if (false) {
+#else
+                if (cons_active) {
+#endif
                     float g[FC2];
 #pragma unroll
                     for (int k = 0; k < FC2; ++k) g[k] = P.b2[k];
-                    const float4* mrow = reinterpret_cast<const float4*>(&S.ms[cl3][0][0]);
+                    const float4* mrow = reinterpret_cast<const float4*>(&S.ms[buf][ccol][0][0]);
 #pragma unroll
-                    for (int j = 0; j < FC1; ++j) {
+                    for (int j = 0; j < FC1; ++j) {                       // fully unrolled: W2/b1 are static constant-bank operands
                         const float4 m0 = mrow[j * 3], m1 = mrow[j * 3 + 1], m2 = mrow[j * 3 + 2];
-                        float a = P.b1[j];
-                        a = fmaf(m0.x, Ee[0], a); a = fmaf(m0.y, Ee[1], a);
-                        a = fmaf(m0.z, Ee[2], a); a = fmaf(m0.w, Ee[3], a);
-                        a = fmaf(m1.x, Ee[4], a); a = fmaf(m1.y, Ee[5], a);
-                        a = fmaf(m1.z, Ee[6], a); a = fmaf(m1.w, Ee[7], a);
-                        a = fmaf(m2.x, Ee[8], a); a = fmaf(m2.y, Ee[9], a);
-                        a = fmaf(m2.z, Ee[10], a); a = fmaf(m2.w, Ee[11], a);
-                        a = fmaxf(a, 0.f);
+                        float a0 = fmaf(m0.x, Ee[0], P.b1[j]);
+                        float a1 = m1.x * Ee[4];
+                        float a2 = m2.x * Ee[8];
+                        a0 = fmaf(m0.y, Ee[1], a0); a1 = fmaf(m1.y, Ee[5], a1); a2 = fmaf(m2.y, Ee[9], a2);
+                        a0 = fmaf(m0.z, Ee[2], a0); a1 = fmaf(m1.z, Ee[6], a1); a2 = fmaf(m2.z, Ee[10], a2);
+                        a0 = fmaf(m0.w, Ee[3], a0); a1 = fmaf(m1.w, Ee[7], a1); a2 = fmaf(m2.w, Ee[11], a2);
+                        const float a = fmaxf(a0 + (a1 + a2), 0.f);
 #pragma unroll
                         for (int k = 0; k < FC2; ++k) g[k] = fmaf(P.W2[k * FC1 + j], a, g[k]);
                     }
@@ -165,24 +251,26 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
 #pragma unroll
                     for (int k = 0; k < FC2; k += 2)
                         dst[k / 2] = make_float2(fmaxf(g[k], 0.f), fmaxf(g[k + 1], 0.f));
-                } else if (e < EMB + (IN0P - IN0) / 4) {          // zero the k-padding of the row
-                    reinterpret_cast<float4*>(urow + IN0)[e - EMB] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (zt >= 0 && zt < 3) {                     // zero the k-padding of this column's row
+                    reinterpret_cast<float4*>(urow + IN0)[zt] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (ch + 2 < NCHUNK) bar_arrive(BAR_EMPTY + buf);
             }
         }
+        __syncthreads();                           // window done: lists / M buffers reusable
     }
 }
 
 cudaError_t front_setup() {
     return cudaFuncSetAttribute(front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(FrontSmem));
+                                (int)sizeof(FrontSmem) + 128);
 }
 
 cudaError_t launch_front(const FrontConst& fc, const uint8_t* x, const float* packed, float* u, int nwin,
                          int* status, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
     int grid = nwin < num_sms ? nwin : num_sms;
-    front_kernel<<<grid, FR_THREADS, sizeof(FrontSmem), s>>>(fc, x, packed, u, nwin, status);
+    front_kernel<<<grid, FR_THREADS, sizeof(FrontSmem) + 128, s>>>(fc, x, packed, u, nwin, status);
     return cudaGetLastError();
 }
 

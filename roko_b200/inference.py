@@ -1,0 +1,203 @@
+"""Drop-in for the reference's ``roko/inference.py`` entry point (same CLI, same ``.hdf5`` feature
+and ``.pth`` weight formats, same FASTA output), with the model call replaced by the B200 path.
+
+    python -m roko_b200.inference <data.hdf5> <model.pth> <out.fasta> [--t workers] [--b batch]
+
+Reference behaviour mirrored (file:line in /root/reference/roko/inference.py):
+  * alphabet / decoding                                              :14-17
+  * ``InferenceDataset``: flat index over every group except ``contigs`` (``attrs['size']``),
+    contig drafts from ``/contigs/<name>.attrs['seq'|'len']``, lazy per-process file handle   :27-87
+  * ``infer``: load state_dict, eval, batches in file order, argmax labels, one vote per
+    (contig, (rpos, ins)) and label                                   :90-127
+  * stitching: sort positions, drop leading insertion slots, majority base per position with
+    ``Counter.most_common`` tie behaviour (first label seen wins), skip '*', splice the draft's
+    prefix and suffix                                                 :129-151
+  * FASTA via ``SeqIO.write`` of ``SeqRecord(seq, id=contig)``        :149-154
+
+Differences, all on the host side of the boundary: windows stay uint8 end to end (the reference
+widens to int64 before the copy, :113); labels come back as uint8 from the fused argmax; the
+per-position Python ``Counter`` loop (:119-124, ~44 ms per 128-window batch) is a vectorised
+numpy scatter with the same tie rule.  ``h5py`` is needed to read real files (it is not in this
+image; tests inject an in-memory stand-in); biopython is not needed.
+"""
+import argparse
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from .rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+
+GAP = "*"
+ALPHABET = "ACGT" + GAP + "N"
+encoding = {v: i for i, v in enumerate(ALPHABET)}
+decoding = {v: k for k, v in encoding.items()}
+N_LABELS = 5          # classes the network emits: A C G T *
+MAX_INS = 3           # insertion slots per reference position (reference include/generate.h:22)
+
+
+def _h5():
+    try:
+        import h5py
+        return h5py
+    except ImportError as e:      # pragma: no cover - depends on the image
+        raise RuntimeError("reading .hdf5 feature files needs h5py, which is not installed here") from e
+
+
+class ToTensor:
+    def __call__(self, sample):
+        contig, position, x = sample
+        return contig, position, torch.from_numpy(np.ascontiguousarray(x))
+
+
+class InferenceDataset(Dataset):
+    """Flat view of the windows of a feature file (schema: SURVEY.md App. C, reference data.py:40-48)."""
+
+    def __init__(self, path, transform=None, h5=None):
+        self.path, self.transform, self._h5mod = path, transform, h5
+        self.contigs, self.idx, self.size, self.fd = {}, [], 0, None
+        fd = self._open()
+        try:
+            for g in fd.keys():
+                if g == "contigs":
+                    continue
+                n = int(fd[g].attrs["size"])
+                self.idx.extend((g, j) for j in range(n))
+                self.size += n
+            for k in fd["contigs"]:
+                grp = fd["contigs"][k]
+                self.contigs[str(k)] = (grp.attrs["seq"], grp.attrs["len"])
+        finally:
+            fd.close()
+
+    def _open(self):
+        return (self._h5mod or _h5()).File(self.path, "r")
+
+    def __getitem__(self, i):
+        if self.fd is None:
+            self.fd = self._open()          # lazily, once per DataLoader worker process
+        g, p = self.idx[i]
+        group = self.fd[g]
+        sample = (group.attrs["contig"], group["positions"][p], group["examples"][p])
+        return self.transform(sample) if self.transform else sample
+
+    def __len__(self):
+        return self.size
+
+    def close_fd(self):
+        if self.fd is not None:
+            self.fd.close()
+            self.fd = None
+
+
+class VoteTable:
+    """Votes per (contig, (rpos, ins)) with ``Counter`` semantics, vectorised.
+
+    ``counts[slot, label]`` and the global sequence number of each label's first vote are kept so
+    that ties resolve exactly like ``Counter.most_common(1)`` in the reference (:141): among the
+    labels with the highest count the one that was voted first wins.
+    """
+
+    def __init__(self):
+        self.tables = {}        # contig -> (slot_keys dict grows lazily) ; implemented as sparse dict of arrays
+        self.seq = 0
+
+    def add(self, contig, pos, labels):
+        """pos (n,2) int64 [(rpos, ins)], labels (n,) uint8 -- in window/position order."""
+        t = self.tables.get(contig)
+        if t is None:
+            t = self.tables[contig] = {"keys": np.empty(0, np.int64), "counts": np.zeros((0, N_LABELS), np.int32),
+                                       "first": np.zeros((0, N_LABELS), np.int64)}
+        key = pos[:, 0].astype(np.int64) * (MAX_INS + 1) + pos[:, 1].astype(np.int64)
+        new = np.setdiff1d(key, t["keys"])                       # sorted unique
+        if new.size:
+            keys = np.concatenate([t["keys"], new])
+            order = np.argsort(keys, kind="stable")
+            t["keys"] = keys[order]
+            t["counts"] = np.concatenate([t["counts"], np.zeros((new.size, N_LABELS), np.int32)])[order]
+            t["first"] = np.concatenate([t["first"], np.full((new.size, N_LABELS), np.iinfo(np.int64).max)])[order]
+        slot = np.searchsorted(t["keys"], key)
+        lab = labels.astype(np.int64)
+        np.add.at(t["counts"], (slot, lab), 1)
+        np.minimum.at(t["first"], (slot, lab), self.seq + np.arange(key.size, dtype=np.int64))
+        self.seq += key.size
+
+    def consensus(self, contig):
+        """[(rpos, ins)] sorted and the winning label per position."""
+        t = self.tables[contig]
+        counts, first = t["counts"], t["first"]
+        best = counts.max(axis=1, keepdims=True)
+        cand = np.where(counts == best, first, np.iinfo(np.int64).max)
+        winner = cand.argmin(axis=1)
+        keys = t["keys"]
+        return np.stack([keys // (MAX_INS + 1), keys % (MAX_INS + 1)], axis=1), winner
+
+
+def stitch(contig_seq, positions, winners):
+    """inference.py:129-147 for one contig: positions sorted [(rpos, ins)], winners label ids."""
+    keep = np.flatnonzero(positions[:, 1] == 0)
+    if keep.size == 0:
+        raise IndexError("no reference-anchored position for contig")     # the reference raises here too (pos_sorted[0])
+    start = keep[0]                                                       # dropwhile(ins != 0)
+    positions, winners = positions[start:], winners[start:]
+    first, last = int(positions[0, 0]), int(positions[-1, 0])
+    body = "".join(decoding[int(w)] for w in winners if decoding[int(w)] != GAP)
+    return contig_seq[:first] + body + contig_seq[last + 1:]
+
+
+def write_fasta(records, path):
+    """What ``SeqIO.write(records, f, 'fasta')`` emits for ``SeqRecord(Seq(s), id=c)``: the default
+    description ``<unknown description>`` follows the id, sequence wrapped at 60 columns."""
+    with open(path, "w") as f:
+        for name, seq in records:
+            f.write(f">{name} <unknown description>\n")
+            for i in range(0, len(seq), 60):
+                f.write(seq[i:i + 60] + "\n")
+
+
+def infer(data, model_path, out, workers=0, batch_size=128, h5=None, device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("roko_b200.inference needs a CUDA (sm_100a) device: the model path has no CPU fallback")
+    device = torch.device(device or "cuda:0")
+
+    model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)
+    model.load_state_dict(torch.load(model_path, map_location=device))
+    model.eval()
+
+    dataset = InferenceDataset(data, transform=ToTensor(), h5=h5)
+    dataloader = DataLoader(dataset, batch_size=batch_size, shuffle=False, num_workers=workers)
+    votes = VoteTable()
+
+    print("Inference started")
+    with torch.no_grad():
+        for i, (c, pos, x) in enumerate(dataloader):
+            y = model.predict(x.to(device, non_blocking=True)).cpu().numpy()      # uint8 labels, fused argmax
+            pos = pos.numpy()
+            c = np.asarray(c)
+            for contig in dict.fromkeys(c.tolist()):                              # contigs in order of appearance
+                sel = np.flatnonzero(c == contig)
+                votes.add(contig, pos[sel].reshape(-1, 2), y[sel].reshape(-1))
+            if (i + 1) % 100 == 0:
+                print(f"{i + 1} batches processed")
+
+    records = []
+    for contig in votes.tables:
+        positions, winners = votes.consensus(contig)
+        records.append((contig, stitch(dataset.contigs[contig][0], positions, winners)))
+    write_fasta(records, out)
+    return records
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("data", type=str)
+    parser.add_argument("model", type=str)
+    parser.add_argument("out", type=str)
+    parser.add_argument("--t", type=int, default=0)
+    parser.add_argument("--b", type=int, default=128)
+    args = parser.parse_args()
+    infer(args.data, args.model, args.out, args.t, args.b)
+
+
+if __name__ == "__main__":
+    main()

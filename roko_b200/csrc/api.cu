@@ -50,6 +50,7 @@ struct roko_b200_model {
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
     bool use_tc = true;             // tcgen05 3xTF32 projection (ROKO_B200_PROJ=ffma selects the FFMA SGEMM)
+    int rec_tc_min = 256;           // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never)
     FrontConst fc;
     struct Slot {
         cudaStream_t stream = nullptr;
@@ -98,7 +99,12 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
             else
                 CU(launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s));
             if (ev) CU(cudaEventRecord(ev[2 + 2 * l], s));
-            CU(launch_rec(gi, pk + pk_whh(l, 0), dstride, pk + pk_bhn(l, 0), outs[l], nc, m->num_sms, s));
+            // (>= 64 windows also keeps rec_tc's unguarded gi reads of a ragged last group inside the scratch)
+            if (m->rec_tc_min > 0 && nc >= m->rec_tc_min && nc >= 64)
+                CU(launch_rec_tc(gi, pk + pk_rtc(l, 0), pk + pk_rtc(l, 0) + RTC_W, (size_t)RTC_DIR,
+                                 pk + pk_rtc(l, 0) + 2 * RTC_W, outs[l], nc, m->num_sms, s));
+            else
+                CU(launch_rec(gi, pk + pk_whh(l, 0), dstride, pk + pk_bhn(l, 0), outs[l], nc, m->num_sms, s));
             if (taps && taps->gru[l])
                 CU(cudaMemcpyAsync(taps->gru[l], outs[l], (size_t)rows * OUT_W * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
@@ -174,6 +180,8 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = front_setup();
     if (e == cudaSuccess) e = rec_setup();
     if (e == cudaSuccess) e = proj_tc_setup();
+    if (e == cudaSuccess) e = rec_tc_setup();
+    if (const char* rt = getenv("ROKO_B200_REC_TC_MIN")) m->rec_tc_min = atoi(rt);
     {
         const char* pj = getenv("ROKO_B200_PROJ");
         m->use_tc = !(pj && strcmp(pj, "ffma") == 0);

@@ -91,7 +91,14 @@ __host__ __device__ constexpr int pk_wtc(int l) {
     for (int i = 0; i < l; ++i) off += pk_wtc_size(i);
     return off;
 }
-constexpr int PK_TOTAL = pk_wtc(LAYERS);
+// tensor-core recurrence operands per (layer, direction) -- see rec_tc.cu:
+//   WHI  [384][128] tf32-rounded W_hh, row major (goes to tensor memory)
+//   WLO  W_hh - WHI as a ready-to-copy shared-memory image [gate tile][k atom][128 rows][128 B swizzled]
+//   BHN  [128]
+constexpr int RTC_W = G3 * HID;                  // 49 152
+constexpr int RTC_DIR = 2 * RTC_W + HID;         // floats per direction
+__host__ __device__ constexpr int pk_rtc(int l, int d) { return pk_wtc(LAYERS) + (l * 2 + d) * RTC_DIR; }
+constexpr int PK_TOTAL = pk_rtc(LAYERS, 0);
 
 // ---- workspace per window (floats) ------------------------------------------------------------
 constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
@@ -116,6 +123,9 @@ cudaError_t launch_proj(const float* A, int K, const float* W, const float* bias
 cudaError_t launch_proj_tc(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
                            cudaStream_t s);
 cudaError_t proj_tc_setup();
+cudaError_t launch_rec_tc(const float* gi, const float* whi_d0, const float* wlo_d0, size_t dir_stride,
+                          const float* bhn_d0, float* out, int nwin, int num_sms, cudaStream_t s);
+cudaError_t rec_tc_setup();
 cudaError_t launch_rec(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
                        float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t launch_head(const float* h, const float* w4, const float* b4, float* logits, uint8_t* labels,

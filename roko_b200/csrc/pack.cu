@@ -49,6 +49,28 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) 
     }
     if (p < PK_B4) { int i = p - PK_W4; return i < CLASSES * OUT_W ? raw[RAW_W4 + i] : 0.f; }
     if (p < pk_wtc(0)) { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
+    if (p >= pk_rtc(0, 0)) {   // tensor-core recurrence operands (rec_tc.cu)
+        int i = p - pk_rtc(0, 0);
+        const int ld = i / RTC_DIR, l = ld / 2, d = ld % 2;
+        i %= RTC_DIR;
+        if (i >= 2 * RTC_W) return raw[raw_bhh(l, d) + 2 * HID + (i - 2 * RTC_W)];      // b_hn
+        int row, k;
+        const bool lo = i >= RTC_W;
+        if (!lo) { row = i / HID; k = i % HID; }
+        else {
+            const int ob = (i - RTC_W) * 4;
+            const int mt = ob / 65536, rem = ob % 65536, katom = rem / 16384, rem2 = rem % 16384;
+            const int rgrp = rem2 / 1024, within = rem2 % 1024;
+            const int r8 = within / 128, pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+            row = mt * HID + rgrp * 8 + r8;
+            k = katom * 32 + ((pchunk ^ r8) * 4) + w4;
+        }
+        const float v = raw[raw_whh(l, d) + row * HID + k];
+        unsigned hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        const float hi = __uint_as_float(hb);
+        return lo ? v - hi : hi;
+    }
     {   // tf32 hi/lo images of W_ih in the swizzled shared-memory layout of proj_tc.cu
         int l = 0;
         while (l + 1 < LAYERS && p >= pk_wtc(l + 1)) ++l;

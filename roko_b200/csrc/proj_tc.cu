@@ -25,7 +25,7 @@ constexpr int A_IMG_BYTES = TC_BM * TC_BK * 4;          // 16 KB
 constexpr int W_IMG_BYTES = TC_BN * TC_BK * 4;          // 32 KB
 constexpr int STAGE_BYTES = 2 * A_IMG_BYTES + 2 * W_IMG_BYTES;
 constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;       // the whole tensor memory: the allocation then starts at column 0
 // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -59,12 +59,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// issued from warp-uniform code (operands stay in uniform registers); only the elected lane executes it
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t elected) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+        "{\n\t.reg .pred p, pe;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -196,28 +202,30 @@ proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, cons
             }
         }
     } else {
-        // ------------------------------- MMA issuer -------------------------------------------------
-        if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb & 1;
-                const uint32_t ph = (kb >> 1) & 1;
-                mbar_wait(BAR(s), ph);
-                mbar_wait(BAR(2 + s), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = sbase + s * STAGE_BYTES, a_lo = a_hi + A_IMG_BYTES;
-                const uint32_t w_hi = a_lo + A_IMG_BYTES, w_lo = w_hi + W_IMG_BYTES;
+        // ------------------------------- MMA issuer (whole warp, uniform) ---------------------------
+        if (tmem_d != 0) __trap();                                 // all 512 columns are ours -> base 0
+        const uint32_t elected = elect_one();
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb & 1;
+            const uint32_t ph = (kb >> 1) & 1;
+            mbar_wait(BAR(s), ph);
+            mbar_wait(BAR(2 + s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = sbase + s * STAGE_BYTES, a_lo = a_hi + A_IMG_BYTES;
+            const uint32_t w_hi = a_lo + A_IMG_BYTES, w_lo = w_hi + W_IMG_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / 8; ++kk) {           // UMMA K = 8 tf32 = 32 bytes inside the atom
-                    const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
-                    const uint64_t dwh = make_desc(w_hi + kk * 32), dwl = make_desc(w_lo + kk * 32);
-                    umma_tf32(tmem_d, dal, dwh, (kb | kk) ? 1u : 0u);   // small terms first
-                    umma_tf32(tmem_d, dah, dwl, 1u);
-                    umma_tf32(tmem_d, dah, dwh, 1u);
-                }
-                umma_commit(BAR(4 + s));                           // frees the stage when these MMAs retire
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {               // UMMA K = 8 tf32 = 32 bytes inside the atom
+                const uint64_t dah = make_desc(a_hi + kk * 32), dal = make_desc(a_lo + kk * 32);
+                const uint64_t dwh = make_desc(w_hi + kk * 32), dwl = make_desc(w_lo + kk * 32);
+                umma_tf32(0u, dal, dwh, (kb | kk) ? 1u : 0u, elected);   // small terms first
+                umma_tf32(0u, dah, dwl, 1u, elected);
+                umma_tf32(0u, dah, dwh, 1u, elected);
             }
-            umma_commit(BAR(6));                                   // accumulator complete
+            if (elected) umma_commit(BAR(4 + s));                  // frees the stage when these MMAs retire
+            __syncwarp();
         }
+        if (elected) umma_commit(BAR(6));                          // accumulator complete
+        __syncwarp();
     }
     __syncthreads();
     if (warp == 5) {

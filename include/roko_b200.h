@@ -66,9 +66,10 @@ int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, f
                           uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The loop body of roko/inference.py:111-117 for HOST buffers: for each batch of `batch` windows
- * copy x to the device, run the path, copy labels (and logits if not NULL) back.  Batches are
- * pipelined over internal streams; returns after everything has landed in the host buffers.
- * Pinned host memory makes the copies asynchronous. */
+ * copy x to the device, run the path, copy labels (and logits if not NULL) back.  Windows are
+ * independent, so consecutive batches are coalesced into device passes of up to
+ * ROKO_B200_SUPERBATCH (default 2368) windows, pipelined over internal streams; returns after
+ * everything has landed in the host buffers.  Pinned host memory makes the copies asynchronous. */
 int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_windows, int batch,
                          uint8_t* labels_host, float* logits_host);
 

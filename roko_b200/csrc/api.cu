@@ -50,6 +50,7 @@ struct roko_b200_model {
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
     bool use_tc = true;             // tcgen05 3xTF32 projection (ROKO_B200_PROJ=ffma selects the FFMA SGEMM)
+    int superbatch = 2368;          // windows per device pass of infer_host (148 SMs x 16; ROKO_B200_SUPERBATCH)
     int rec_tc_min = 256;           // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never)
     FrontConst fc;
     struct Slot {
@@ -182,6 +183,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = proj_tc_setup();
     if (e == cudaSuccess) e = rec_tc_setup();
     if (const char* rt = getenv("ROKO_B200_REC_TC_MIN")) m->rec_tc_min = atoi(rt);
+    if (const char* sb = getenv("ROKO_B200_SUPERBATCH")) m->superbatch = atoi(sb) > 0 ? atoi(sb) : 1;
     {
         const char* pj = getenv("ROKO_B200_PROJ");
         m->use_tc = !(pj && strcmp(pj, "ffma") == 0);
@@ -284,10 +286,16 @@ int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_
     if (n_windows == 0) return ROKO_B200_OK;
     if (!x_host || !labels_host) return fail(ROKO_B200_EARG, "x_host / labels_host is NULL%s%s");
     DeviceGuard g(m->device);
-    if (int rc = ensure_slots(m, batch)) return rc;
+    // Windows are independent, so the caller's batch size is only a lower bound on the granularity:
+    // consecutive batches are coalesced into device passes of up to `superbatch` windows (a multiple of
+    // the caller's batch), which is what lets the tensor-core recurrence fill the machine.
+    long long pass = batch;
+    if (m->superbatch > batch) pass = (long long)(m->superbatch / batch) * batch;
+    if (pass > n_windows) pass = n_windows;
+    if (int rc = ensure_slots(m, (int)pass)) return rc;
     int i = 0;
-    for (long long b0 = 0; b0 < n_windows; b0 += batch, ++i) {
-        const int nb = (n_windows - b0) < batch ? (int)(n_windows - b0) : batch;
+    for (long long b0 = 0; b0 < n_windows; b0 += pass, ++i) {
+        const int nb = (n_windows - b0) < pass ? (int)(n_windows - b0) : (int)pass;
         auto& sl = m->slot[i % NSLOT];
         // stream order already protects the slot's device buffers against the previous use
         CU(cudaMemcpyAsync(sl.x, x_host + (size_t)b0 * WIN_BYTES, (size_t)nb * WIN_BYTES, cudaMemcpyHostToDevice, sl.stream));

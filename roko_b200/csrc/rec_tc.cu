@@ -103,8 +103,8 @@ rec_tc_kernel(const float* __restrict__ gi, const float* __restrict__ whi0, cons
     unsigned char* s_hhi = smem + RT_WLO_BYTES;                  // 16 KB   [katom][32 rows][128 B]
     unsigned char* s_hlo = s_hhi + RT_H_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_hlo + RT_H_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    const uint32_t bar_w = rt_smem_u32(bars), bar_h = bar_w + 8, bar_d = bar_w + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    const uint32_t bar_w = rt_smem_u32(bars), bar_h = bar_w + 8, bar_d = bar_w + 16, bar_d2 = bar_w + 24;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.x & 1;
@@ -115,6 +115,7 @@ rec_tc_kernel(const float* __restrict__ gi, const float* __restrict__ whi0, cons
         rt_mbar_init(bar_w, 1);
         rt_mbar_init(bar_h, RT_GATE_THREADS);
         rt_mbar_init(bar_d, 1);
+        rt_mbar_init(bar_d2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == RT_GATE_THREADS / 32) {
@@ -206,15 +207,20 @@ rec_tc_kernel(const float* __restrict__ gi, const float* __restrict__ whi0, cons
                 uint32_t dr[RT_WPT], dz[RT_WPT], dn[RT_WPT];
                 RT_TMEM_LD8(dr, t_lane);
                 RT_TMEM_LD8(dz, t_lane + RT_N);
-                RT_TMEM_LD8(dn, t_lane + 2 * RT_N);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#ifdef RT_SKIP_GATES
-                if (s == 1000)
-#endif
+                float rr[RT_WPT], zz[RT_WPT];                     // r, z while the n-gate MMAs are still running
 #pragma unroll
                 for (int b = 0; b < RT_WPT; ++b) {
-                    const float r = rt_sigmoid(g_r[b] + __uint_as_float(dr[b]));
-                    const float z = rt_sigmoid(g_z[b] + __uint_as_float(dz[b]));
+                    rr[b] = rt_sigmoid(g_r[b] + __uint_as_float(dr[b]));
+                    zz[b] = rt_sigmoid(g_z[b] + __uint_as_float(dz[b]));
+                }
+                rt_mbar_wait(bar_d2, ph_d ^ 1);                   // same phase sequence as bar_d
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                RT_TMEM_LD8(dn, t_lane + 2 * RT_N);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int b = 0; b < RT_WPT; ++b) {
+                    const float r = rr[b], z = zz[b];
                     const float n = rt_tanh(g_n[b] + r * (__uint_as_float(dn[b]) + bhn));
                     const float h = fmaf(z, hprev[b] - n, n);
                     hprev[b] = h;
@@ -250,24 +256,28 @@ rec_tc_kernel(const float* __restrict__ gi, const float* __restrict__ whi0, cons
                 rt_mbar_wait(bar_h, ph_h); ph_h ^= 1;
                 if (s == COLS) break;                             // the last arrival only closes the group
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#ifndef RT_SKIP_MMA
+                // r and z tiles first and committed on their own, so the gate threads can start the two
+                // sigmoids while the n tile is still being multiplied
 #pragma unroll
-                for (int kk = 0; kk < HID / 8; ++kk) {
-                    const uint32_t koff = (uint32_t)(kk >> 2) * (RT_N * 128) + (uint32_t)(kk & 3) * 32;
-                    const uint64_t dbh = rt_desc(b_hi + koff), dbl = rt_desc(b_lo + koff);
+                for (int part = 0; part < 2; ++part) {
 #pragma unroll
-                    for (int mt = 0; mt < 3; ++mt) {              // three independent accumulators interleaved
-                        const uint32_t d = RT_D_COL + mt * RT_N;
-                        const uint64_t dal = rt_desc(a_lo + mt * 65536 + (kk >> 2) * 16384 + (kk & 3) * 32);
-                        const uint32_t a_hi = (uint32_t)(mt * HID + kk * 8);
-                        rt_mma_ss(d, dal, dbh, kk ? 1u : 0u, elected);   // W_lo h_hi   (small terms first)
-                        rt_mma_ts(d, a_hi, dbl, 1u, elected);            // W_hi h_lo
-                        rt_mma_ts(d, a_hi, dbh, 1u, elected);            // W_hi h_hi
+                    for (int kk = 0; kk < HID / 8; ++kk) {
+                        const uint32_t koff = (uint32_t)(kk >> 2) * (RT_N * 128) + (uint32_t)(kk & 3) * 32;
+                        const uint64_t dbh = rt_desc(b_hi + koff), dbl = rt_desc(b_lo + koff);
+#pragma unroll
+                        for (int mt = part ? 2 : 0; mt < (part ? 3 : 2); ++mt) {
+                            const uint32_t d = RT_D_COL + mt * RT_N;
+                            const uint64_t dal = rt_desc(a_lo + mt * 65536 + (kk >> 2) * 16384 + (kk & 3) * 32);
+                            const uint32_t a_hi = (uint32_t)(mt * HID + kk * 8);
+                            rt_mma_ss(d, dal, dbh, kk ? 1u : 0u, elected);   // W_lo h_hi   (small terms first)
+                            rt_mma_ts(d, a_hi, dbl, 1u, elected);            // W_hi h_lo
+                            rt_mma_ts(d, a_hi, dbh, 1u, elected);            // W_hi h_hi
+                        }
                     }
+                    if (elected)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     ::"r"(part ? bar_d2 : bar_d) : "memory");
                 }
-#endif
-                if (elected)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_d) : "memory");
                 __syncwarp();
             }
         }

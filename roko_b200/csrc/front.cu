@@ -9,42 +9,41 @@
 //     g[p][e][k] = relu(b2[k] + sum_j W2[k][j] * a[p][e][j])
 //
 // One persistent CTA per SM walks windows.  A window (18 000 contiguous bytes) arrives by a single
-// TMA bulk copy, double buffered so the next window lands while this one computes.  Per window:
-//   sort      all 16 warps: counting sort of each column's 200 reads by code -> per-code read
-//             lists, each padded to a multiple of 4 with the index of an all-zero W1T row
-//   then a warp-specialised pipeline over chunks of 6 columns, double buffered through M:
-//   producers (6 warps) thread = (column, 4 consecutive j): sum W1T rows over each list
-//             (LDS.128 + 4 FADD per read) -> M chunk in shared memory
-//   consumers (10 warps) thread = (column, e): a and g entirely in registers; W2/b1/b2 come from
-//             the kernel-parameter constant bank, M rows are warp-broadcast LDS.128
-// Producers and consumers meet only at named barriers (full/empty per M buffer).
+// TMA bulk copy, double buffered so the next window lands while this one computes.  Inside a
+// window every WARP owns whole columns and runs them end to end with warp-level sync only:
+//   sort      counting sort of the column's 200 reads by code (packed-byte histograms + shuffle
+//             scan) -> per-code read lists, padded to a multiple of 4 with the index of an all-zero
+//             W1T row
+//   gather    lane = 4 consecutive j (25 lanes): sum W1T rows over each list (LDS.128 + 4 FADD per
+//             read) -> the column's M (100 x 12) in the warp's private shared-memory slab
+//   a, g      lane = two embedding dims (e, e+25): a and g entirely in registers; W2/b1/b2 are
+//             constant-bank operands (kernel parameters), M rows are warp-broadcast LDS.128
+// The 16 warps of a CTA drift apart, so the latency-bound gather of some warps overlaps the
+// FFMA-bound a/g stage of others without any block-level barrier (an earlier producer/consumer
+// split on named barriers serialised: 0.10 + 0.10 = 0.21 ms per 128 windows).
 #include "common.cuh"
 
 namespace roko {
 
 constexpr int FR_THREADS = 512;
-constexpr int FR_PROD = 192;                  // producer threads (6 warps)
-constexpr int FR_CONS = FR_THREADS - FR_PROD; // consumer threads (10 warps)
-constexpr int CC = 5;                         // columns per chunk: 125 producer tasks, 5 x 64 consumer threads
-constexpr int NCHUNK = COLS / CC;             // 18
+constexpr int FR_WARPS = FR_THREADS / 32;
 constexpr int LIST_LEN = 240;                 // 200 reads + up to 3 pads for each of 12 codes
-constexpr int JQ = FC1 / 4;
-static_assert(COLS % CC == 0 && CC * JQ <= FR_PROD && CC * 64 <= FR_CONS, "role sizes");
+constexpr int JQ = FC1 / 4;                   // 25 gather lanes
+constexpr int EH = EMB / 2;                   // 25 a/g lanes, two embedding dims each
 
-struct FrontSmem {
-    float w1t[W1T_ROWS * FC1];                     // 80 400 B  [r][j], row 200 zero
-    float ms[2][CC][FC1][NCODES];                  // 48 000 B  double-buffered M chunk
-    alignas(16) uint8_t xs[2][READS * COLS];      // 36 000 B  double-buffered window, [read][col]
-    alignas(16) uint8_t lists[COLS][LIST_LEN];     // 21 600 B  (240 is a multiple of 8: uint2 loads stay aligned)
-    uint8_t starts[COLS][16];                      //  1 440 B
-    alignas(8) unsigned long long xbar[2];         // TMA arrival barriers of the two window buffers
+struct FrontWarp {                            // private to one warp
+    float m[FC1][NCODES];                     // 4 800 B
+    alignas(16) uint8_t list[LIST_LEN];       //   240 B
+    uint8_t start[16];
 };
 
-// named barrier ids (0 is __syncthreads)
-constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
-
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(FR_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(FR_THREADS) : "memory"); }
+struct FrontSmem {
+    float w1t[W1T_ROWS * FC1];                // 80 400 B  [r][j], row 200 zero
+    FrontWarp wp[FR_WARPS];                   // 80 896 B
+    alignas(16) float w2t[FC1][12];           //  4 800 B  [j] -> W2[0..9][j], b1[j], 0
+    alignas(16) uint8_t xs[2][READS * COLS];  // 36 000 B  double-buffered window, [read][col]
+    alignas(8) unsigned long long xbar[2];    // TMA arrival barriers of the two window buffers
+};
 
 __device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,7 +56,7 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w0, uint32_t w1, uint32_t w
     return (w >> ((code & 3u) * 8u)) & 0xffu;
 }
 
-__device__ __forceinline__ void sort_column(FrontSmem& S, const uint8_t* xs, int p, int lane, int* status) {
+__device__ __forceinline__ void sort_column(FrontWarp& W, const uint8_t* xs, int p, int lane, int* status) {
     uint32_t codes[7];
     uint32_t h0 = 0, h1 = 0, h2 = 0;               // my histogram
     uint32_t rank[7];                              // rank of read i among my earlier reads of the same code
@@ -93,24 +92,24 @@ __device__ __forceinline__ void sort_column(FrontSmem& S, const uint8_t* xs, int
         const uint32_t cnt = byte_of(tot0, tot1, tot2, c);
         const uint32_t sh = (c & 3) * 8;
         if (c < 4) st0 |= run << sh; else if (c < 8) st1 |= run << sh; else st2 |= run << sh;
-        if (lane == 0) S.starts[p][c] = (uint8_t)run;
+        if (lane == 0) W.start[c] = (uint8_t)run;
         const uint32_t end = run + ((cnt + 3u) & ~3u);
-        if (lane < (int)(end - run - cnt)) S.lists[p][run + cnt + lane] = (uint8_t)READS;   // pad -> zero row
+        if (lane < (int)(end - run - cnt)) W.list[run + cnt + lane] = (uint8_t)READS;   // pad -> zero row
         run = end;
     }
-    if (lane == 0) S.starts[p][NCODES] = (uint8_t)run;
+    if (lane == 0) W.start[NCODES] = (uint8_t)run;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const uint32_t code = codes[i];
         if (code < NCODES) {
             const uint32_t pos = byte_of(st0, st1, st2, code) + byte_of(e0, e1, e2, code) + rank[i];
-            S.lists[p][pos] = (uint8_t)(lane * 7 + i);
+            W.list[pos] = (uint8_t)(lane * 7 + i);
         }
     }
 }
 
-__device__ __forceinline__ void build_m(FrontSmem& S, int buf, int cl, int p, int jq) {
-    const float4* w4 = reinterpret_cast<const float4*>(S.w1t);
+__device__ __forceinline__ void build_m(const float* w1t, FrontWarp& W, int jq) {
+    const float4* w4 = reinterpret_cast<const float4*>(w1t);
     float4 acc[NCODES];
     auto add4 = [&](float4& a, uint32_t q) {       // four list entries -> four W1T rows
         const float4 v0 = w4[(q & 0xffu) * JQ + jq];
@@ -125,12 +124,12 @@ __device__ __forceinline__ void build_m(FrontSmem& S, int buf, int cl, int p, in
 #pragma unroll
     for (int c = 0; c < NCODES; ++c) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int i0 = S.starts[p][c], i1 = S.starts[p][c + 1];
+        const int i0 = W.start[c], i1 = W.start[c + 1];
 #pragma unroll 1
-        for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&S.lists[p][i]));
+        for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
         acc[c] = a;
     }
-    float4* m = reinterpret_cast<float4*>(&S.ms[buf][cl][4 * jq][0]);
+    float4* m = reinterpret_cast<float4*>(&W.m[4 * jq][0]);
     m[0] = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
     m[1] = make_float4(acc[4].x, acc[5].x, acc[6].x, acc[7].x);
     m[2] = make_float4(acc[8].x, acc[9].x, acc[10].x, acc[11].x);
@@ -163,6 +162,10 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
         float4* dst = reinterpret_cast<float4*>(S.w1t);
         for (int i = tid; i < W1T_ROWS * FC1 / 4; i += FR_THREADS) dst[i] = src[i];
     }
+    for (int i = tid; i < FC1 * 12; i += FR_THREADS) {
+        const int j = i / 12, k = i % 12;
+        S.w2t[j][k] = k < FC2 ? P.W2[k * FC1 + j] : (k == FC2 ? P.b1[j] : 0.f);
+    }
     __syncthreads();
     auto fetch_window = [&](int w, int buf) {      // one thread: TMA bulk copy of a whole window
         const uint32_t bar = fr_smem_u32(&S.xbar[buf]);
@@ -172,21 +175,19 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     };
     if (tid == 0 && (int)blockIdx.x < nwin) fetch_window(blockIdx.x, 0);
 
-    // consumer identity: (column within chunk, embedding dim)
-    // Consumers take the LOW warp ids, producers the HIGH ones: the warp arbiter favours high warp
-    // ids, so the latency-bound gather keeps running underneath the FFMA-bound consumers (measured:
-    // with the roles the other way round the two phases serialised, 0.225 ms -> see DESIGN.md).
-    const int ct = tid;
-    const bool is_cons = tid < FR_CONS;
-    const int pt = tid - FR_CONS;                  // producer thread index
-    // two warps per column (lanes 50..52 of the pair zero the k-padding): every M-row LDS.128 is a
-    // pure warp broadcast = one shared-memory wavefront
-    const int ccol = is_cons ? ct >> 6 : 0, e = is_cons ? ct & 63 : 0;
-    const bool cons_active = is_cons && ccol < CC && e < EMB;
-    const int zt = (is_cons && ccol < CC) ? e - EMB : -1;
-    float Ee[NCODES];
+    FrontWarp& W = S.wp[warp];
+    // a/g stage: lane l < 25 owns embedding dims l and l + 25.  Lanes 25..31 run the same loop on a
+    // duplicate index and store nothing: keeping the loop in warp-uniform control flow lets the
+    // compiler index W2/b1 in the constant bank through the uniform datapath with a rolled loop
+    // (a fully unrolled body is 88 KB of code and thrashed the instruction cache: 2.1 stalled warps
+    // per issue on "no instruction").
+    const int el = lane < EH ? lane : lane - 8;
+    float E0[NCODES], E1[NCODES];
 #pragma unroll
-    for (int c = 0; c < NCODES; ++c) Ee[c] = cons_active ? packed[PK_E + c * EMB + e] : 0.f;
+    for (int c = 0; c < NCODES; ++c) {
+        E0[c] = packed[PK_E + c * EMB + el];
+        E1[c] = packed[PK_E + c * EMB + el + EH];
+    }
 
     int it = 0;
     for (int w = blockIdx.x; w < nwin; w += gridDim.x, ++it) {
@@ -201,63 +202,65 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                 "bra W_%=;\n\t"
                 "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
         }
-#ifndef FR_SKIP_SORT
-        for (int p = warp; p < COLS; p += FR_THREADS / 32) sort_column(S, S.xs[xb], p, lane, status);
-#endif
-        __syncthreads();                           // lists complete; xs[xb^1] (previous window) is free
+        // every warp is past the previous window (barrier at the bottom), so its buffer is free
         if (tid == 0 && w + (int)gridDim.x < nwin) fetch_window(w + gridDim.x, xb ^ 1);
 
-        if (!is_cons) {
-            // ---------------------------- producers: M chunks ------------------------------------
-            const int cl = pt / JQ, jq = pt % JQ;
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                const int buf = ch & 1;
-                if (ch >= 2) bar_sync(BAR_EMPTY + buf);             // consumers released this buffer
-#ifndef FR_SKIP_BUILD
-                if (cl < CC) build_m(S, buf, cl, ch * CC + cl, jq);
-#endif
-                __threadfence_block();
-                bar_arrive(BAR_FULL + buf);
-            }
-        } else {
-            // ---------------------------- consumers: a, g -----------------------------------------
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                const int buf = ch & 1;
-                bar_sync(BAR_FULL + buf);
-                float* urow = u + ((size_t)w * COLS + ch * CC + (ccol < CC ? ccol : 0)) * IN0P;
-#ifdef FR_SKIP_CONS
-                if (false) {
-#else
-                if (cons_active) {
-#endif
-                    float g[FC2];
+        for (int p = warp; p < COLS; p += FR_WARPS) {
+            sort_column(W, S.xs[xb], p, lane, status);
+            __syncwarp();
+            if (lane < JQ) build_m(S.w1t, W, lane);
+            __syncwarp();
+            float* urow = u + ((size_t)w * COLS + p) * IN0P;
+            {
+                float g0[FC2], g1[FC2];
 #pragma unroll
-                    for (int k = 0; k < FC2; ++k) g[k] = P.b2[k];
-                    const float4* mrow = reinterpret_cast<const float4*>(&S.ms[buf][ccol][0][0]);
-#pragma unroll
-                    for (int j = 0; j < FC1; ++j) {                       // fully unrolled: W2/b1 are static constant-bank operands
-                        const float4 m0 = mrow[j * 3], m1 = mrow[j * 3 + 1], m2 = mrow[j * 3 + 2];
-                        float a0 = fmaf(m0.x, Ee[0], P.b1[j]);
-                        float a1 = m1.x * Ee[4];
-                        float a2 = m2.x * Ee[8];
-                        a0 = fmaf(m0.y, Ee[1], a0); a1 = fmaf(m1.y, Ee[5], a1); a2 = fmaf(m2.y, Ee[9], a2);
-                        a0 = fmaf(m0.z, Ee[2], a0); a1 = fmaf(m1.z, Ee[6], a1); a2 = fmaf(m2.z, Ee[10], a2);
-                        a0 = fmaf(m0.w, Ee[3], a0); a1 = fmaf(m1.w, Ee[7], a1); a2 = fmaf(m2.w, Ee[11], a2);
-                        const float a = fmaxf(a0 + (a1 + a2), 0.f);
-#pragma unroll
-                        for (int k = 0; k < FC2; ++k) g[k] = fmaf(P.W2[k * FC1 + j], a, g[k]);
-                    }
-                    float2* dst = reinterpret_cast<float2*>(urow + e * FC2);
-#pragma unroll
-                    for (int k = 0; k < FC2; k += 2)
-                        dst[k / 2] = make_float2(fmaxf(g[k], 0.f), fmaxf(g[k + 1], 0.f));
-                } else if (zt >= 0 && zt < 3) {                     // zero the k-padding of this column's row
-                    reinterpret_cast<float4*>(urow + IN0)[zt] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < FC2; ++k) g0[k] = g1[k] = P.b2[k];
+                const float4* mrow = reinterpret_cast<const float4*>(&W.m[0][0]);
+                const float4* wrow = reinterpret_cast<const float4*>(&S.w2t[0][0]);
+#pragma unroll 4
+                for (int j = 0; j < FC1; ++j) {
+                    const float4 m0 = mrow[j * 3], m1 = mrow[j * 3 + 1], m2 = mrow[j * 3 + 2];
+                    const float4 w0 = wrow[j * 3], w1 = wrow[j * 3 + 1], w2 = wrow[j * 3 + 2];   // W2[0..9][j], b1[j]
+                    // two embedding dims share every load; per dim three independent 4-term chains
+                    float a0 = fmaf(m0.x, E0[0], w2.z), b0 = fmaf(m0.x, E1[0], w2.z);
+                    float a1 = m1.x * E0[4], b1 = m1.x * E1[4];
+                    float a2 = m2.x * E0[8], b2 = m2.x * E1[8];
+                    a0 = fmaf(m0.y, E0[1], a0); b0 = fmaf(m0.y, E1[1], b0);
+                    a1 = fmaf(m1.y, E0[5], a1); b1 = fmaf(m1.y, E1[5], b1);
+                    a2 = fmaf(m2.y, E0[9], a2); b2 = fmaf(m2.y, E1[9], b2);
+                    a0 = fmaf(m0.z, E0[2], a0); b0 = fmaf(m0.z, E1[2], b0);
+                    a1 = fmaf(m1.z, E0[6], a1); b1 = fmaf(m1.z, E1[6], b1);
+                    a2 = fmaf(m2.z, E0[10], a2); b2 = fmaf(m2.z, E1[10], b2);
+                    a0 = fmaf(m0.w, E0[3], a0); b0 = fmaf(m0.w, E1[3], b0);
+                    a1 = fmaf(m1.w, E0[7], a1); b1 = fmaf(m1.w, E1[7], b1);
+                    a2 = fmaf(m2.w, E0[11], a2); b2 = fmaf(m2.w, E1[11], b2);
+                    const float a = fmaxf(a0 + (a1 + a2), 0.f), b = fmaxf(b0 + (b1 + b2), 0.f);
+                    g0[0] = fmaf(w0.x, a, g0[0]); g1[0] = fmaf(w0.x, b, g1[0]);
+                    g0[1] = fmaf(w0.y, a, g0[1]); g1[1] = fmaf(w0.y, b, g1[1]);
+                    g0[2] = fmaf(w0.z, a, g0[2]); g1[2] = fmaf(w0.z, b, g1[2]);
+                    g0[3] = fmaf(w0.w, a, g0[3]); g1[3] = fmaf(w0.w, b, g1[3]);
+                    g0[4] = fmaf(w1.x, a, g0[4]); g1[4] = fmaf(w1.x, b, g1[4]);
+                    g0[5] = fmaf(w1.y, a, g0[5]); g1[5] = fmaf(w1.y, b, g1[5]);
+                    g0[6] = fmaf(w1.z, a, g0[6]); g1[6] = fmaf(w1.z, b, g1[6]);
+                    g0[7] = fmaf(w1.w, a, g0[7]); g1[7] = fmaf(w1.w, b, g1[7]);
+                    g0[8] = fmaf(w2.x, a, g0[8]); g1[8] = fmaf(w2.x, b, g1[8]);
+                    g0[9] = fmaf(w2.y, a, g0[9]); g1[9] = fmaf(w2.y, b, g1[9]);
                 }
-                if (ch + 2 < NCHUNK) bar_arrive(BAR_EMPTY + buf);
+                if (lane < EH) {
+                    float2* d0 = reinterpret_cast<float2*>(urow + lane * FC2);
+                    float2* d1 = reinterpret_cast<float2*>(urow + (lane + EH) * FC2);
+#pragma unroll
+                    for (int k = 0; k < FC2; k += 2) {
+                        d0[k / 2] = make_float2(fmaxf(g0[k], 0.f), fmaxf(g0[k + 1], 0.f));
+                        d1[k / 2] = make_float2(fmaxf(g1[k], 0.f), fmaxf(g1[k + 1], 0.f));
+                    }
+                } else if (lane < EH + 3) {                        // zero the k-padding of the row
+                    reinterpret_cast<float4*>(urow + IN0)[lane - EH] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
+            __syncwarp();                                          // M slab is reused by the next column
         }
-        __syncthreads();                           // window done: lists / M buffers reusable
+        __syncthreads();                                           // window done: its xs buffer may be refilled
     }
 }
 

@@ -81,11 +81,17 @@ __device__ __forceinline__ float tf32_hi(float v) {
     return __uint_as_float(u);
 }
 
-template <int K>
+// CL = CTAs per cluster along the m axis.  The CL CTAs of a cluster compute different row tiles of the
+// same 256 output columns, so they need the same W images: each loads 1/CL of every 64 KB k-block with
+// one multicast TMA that lands in all CL shared memories, cutting the L2 -> SM traffic per CTA from
+// 16 + 64 KB to 16 + 64/CL KB per k-block (the single-CTA version is L2-bandwidth bound).
+template <int K, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const float* __restrict__ bias,
                float* __restrict__ C, int M) {
     constexpr int KB = K / TC_BK;
+    uint32_t cta_rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
@@ -102,7 +108,7 @@ proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, cons
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(BAR(s), 128);        // every A-producer thread arrives
             mbar_init(BAR(2 + s), 1);      // TMA thread's expect_tx arrive
-            mbar_init(BAR(4 + s), 1);      // tcgen05.commit
+            mbar_init(BAR(4 + s), CL);     // one tcgen05.commit from every CTA of the cluster
         }
         mbar_init(BAR(6), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -113,6 +119,10 @@ proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) {   // peers' barriers must be initialised before anyone multicasts into them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
@@ -197,8 +207,17 @@ proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, cons
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb & 1;
                 mbar_wait(BAR(4 + s), ((kb >> 1) & 1) ^ 1);
-                mbar_expect_tx(BAR(2 + s), 2 * W_IMG_BYTES);
-                bulk_g2s(sbase + s * STAGE_BYTES + 2 * A_IMG_BYTES, src + (size_t)kb * 2 * TC_IMG, 2 * W_IMG_BYTES, BAR(2 + s));
+                mbar_expect_tx(BAR(2 + s), 2 * W_IMG_BYTES);      // the full 64 KB lands here, 1/CL from each CTA
+                if (CL == 1) {
+                    bulk_g2s(sbase + s * STAGE_BYTES + 2 * A_IMG_BYTES, src + (size_t)kb * 2 * TC_IMG, 2 * W_IMG_BYTES, BAR(2 + s));
+                } else {
+                    constexpr uint32_t PART = 2 * W_IMG_BYTES / CL;
+                    const uint32_t dst = sbase + s * STAGE_BYTES + 2 * A_IMG_BYTES + cta_rank * PART;
+                    const unsigned char* g = reinterpret_cast<const unsigned char*>(src + (size_t)kb * 2 * TC_IMG) + cta_rank * PART;
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                        ::"r"(dst), "l"(g), "r"(PART), "r"(BAR(2 + s)), "h"((uint16_t)((1u << CL) - 1)) : "memory");
+                }
             }
         }
     } else {
@@ -221,33 +240,73 @@ proj_tc_kernel(const float* __restrict__ A, const float* __restrict__ wimg, cons
                 umma_tf32(0u, dah, dwl, 1u, elected);
                 umma_tf32(0u, dah, dwh, 1u, elected);
             }
-            if (elected) umma_commit(BAR(4 + s));                  // frees the stage when these MMAs retire
+            if (elected) {                                         // frees the stage (in every CTA of the cluster) when these MMAs retire
+                if (CL == 1) umma_commit(BAR(4 + s));
+                else
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(BAR(4 + s)), "h"((uint16_t)((1u << CL) - 1)) : "memory");
+            }
             __syncwarp();
         }
         if (elected) umma_commit(BAR(6));                          // accumulator complete
         __syncwarp();
     }
     __syncthreads();
+    if (CL > 1) {   // nobody leaves while a peer may still multicast into / arrive on this CTA's shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 5) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
 }
 
+static int g_cluster = 1;   // measured on B200: 1 -> 0.948 ms, 2 -> 0.991, 4 -> 1.114 (K=512, 2368 windows): not L2 bound
+
+template <int K, int CL>
+static cudaError_t tc_set_attr() {
+    cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel<K, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    return e;
+}
+
 cudaError_t proj_tc_setup() {
-    cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel<IN0P>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(proj_tc_kernel<OUT_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (const char* c = getenv("ROKO_B200_PROJ_CLUSTER")) g_cluster = atoi(c);
+    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 1;
+    cudaError_t e = tc_set_attr<IN0P, 1>();
+    if (e == cudaSuccess) e = tc_set_attr<OUT_W, 1>();
+    if (e == cudaSuccess) e = tc_set_attr<IN0P, 2>();
+    if (e == cudaSuccess) e = tc_set_attr<OUT_W, 2>();
+    if (e == cudaSuccess) e = tc_set_attr<IN0P, 4>();
+    if (e == cudaSuccess) e = tc_set_attr<OUT_W, 4>();
+    return e;
+}
+
+template <int K, int CL>
+static cudaError_t tc_launch(const float* A, const float* wimg, const float* bias, float* C, int M, cudaStream_t s) {
+    const int mtiles = (M + TC_BM - 1) / TC_BM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(GI_N / TC_BN, ((mtiles + CL - 1) / CL) * CL);   // row tiles padded to whole clusters
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = CL; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, proj_tc_kernel<K, CL>, A, wimg, bias, C, M);
 }
 
 cudaError_t launch_proj_tc(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
                            cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
-    dim3 grid(GI_N / TC_BN, (M + TC_BM - 1) / TC_BM);
-    if (K == IN0P) proj_tc_kernel<IN0P><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(A, wimg, bias, C, M);
-    else if (K == OUT_W) proj_tc_kernel<OUT_W><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(A, wimg, bias, C, M);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (K != IN0P && K != OUT_W) return cudaErrorInvalidValue;
+    const int cl = (M <= TC_BM) ? 1 : g_cluster;                       // a single row tile has nothing to share
+    if (K == IN0P) return cl == 4 ? tc_launch<IN0P, 4>(A, wimg, bias, C, M, s) : cl == 2 ? tc_launch<IN0P, 2>(A, wimg, bias, C, M, s)
+                                                                                          : tc_launch<IN0P, 1>(A, wimg, bias, C, M, s);
+    return cl == 4 ? tc_launch<OUT_W, 4>(A, wimg, bias, C, M, s) : cl == 2 ? tc_launch<OUT_W, 2>(A, wimg, bias, C, M, s)
+                                                                           : tc_launch<OUT_W, 1>(A, wimg, bias, C, M, s);
 }
 
 }  // namespace roko

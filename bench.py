@@ -317,9 +317,38 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{dom_kernel}@B{batch}")
+            tj = json.load(f)
+        # ncu names carry template arguments (rec_kernel<2>, proj_tc_kernel<512, 1>): match on the stem
+        stem = dom_kernel.split("<")[0]
+        cands = [v for k, v in tj.items() if k.split("<")[0].split("@")[0] == stem and k.endswith(f"@B{batch}")
+                 and (("<" not in dom_kernel) or dom_kernel.split("<")[1].split(">")[0].split(",")[0] in k)]
+        traffic = (sum(cands) / len(cands)) if cands else None
     except Exception:
         pass
+
+    # ---- the same work coalesced: consecutive 128-window steps handed to the path as one device pass ---
+    # (windows are independent; this is what predict_host / inference.py do internally)
+    big = min(args.coalesce, P * batch)
+    xb = pool.view(P * batch, READS, COLS)[:big]
+    lb = torch.empty((big, COLS), dtype=torch.uint8, device=dev)
+    ws_big = torch.empty(lib.roko_b200_workspace_bytes(big), dtype=torch.uint8, device=dev)
+    st2 = (ctypes.c_float * 8)()
+    _cabi.check(lib.roko_b200_forward_timed(h.ptr, xb.data_ptr(), big, lb.data_ptr(), ws_big.data_ptr(),
+                                             ws_big.numel(), main.cuda_stream, 10, st2))
+    big_ms = dict(zip(STAGES, [float(v) for v in st2]))
+    big_total = sum(big_ms.values())
+    rec_name = "rec_tc_kernel" if big >= 256 else "rec_kernel"
+    big_kernels = {}
+    for sname, v in big_ms.items():
+        kname = KERNEL_OF[sname] if not sname.startswith("rec") else rec_name
+        d = big_kernels.setdefault(kname, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        d["ms"] += v; d["flops"] += FLOPS[sname] * big; d["launches"] += 1
+    for d in big_kernels.values():
+        d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        d["frac_of_bf16_tensor_peak"] = d["tflops"] / peaks["bf16_tflops_sustained"]
+        d["frac_of_fp32_ffma_peak"] = d["tflops"] / fp32.value if fp32.value else None
+        del d["flops"]
+    del ws_big
 
     if world > 1:
         dist.barrier()
@@ -332,7 +361,9 @@ def run_ours(args):
                 "workload": f"BASELINE configs[1]: batch={batch} synthetic windows (200 reads x 90 cols, uint8 codes 0..11) "
                             "per step on each GPU, random-init weights tests/golden/rand_seed1.pth, labels out (uint8)",
                 "batch": batch, "windows_per_step_all_gpus": batch * world, "parallelism": f"dp{world}",
-                "streams": NS, "l2": f"inputs cycle through a {P * batch * WIN_BYTES / 1e6:.0f} MB pool (> 126 MB L2)",
+                "streams": NS, "e2e_note": "predict_host coalesces consecutive batches into device passes of <= 2368 windows "
+                                           "(windows are independent), so e2e exceeds the per-call batch-128 device number",
+                "l2": f"inputs cycle through a {P * batch * WIN_BYTES / 1e6:.0f} MB pool (> 126 MB L2)",
                 "collectives": "ncclBroadcast weights %d B before timing; label all-gather inside the timed region" % bcast_bytes
                                if world > 1 else "none (1 GPU)",
             },
@@ -353,6 +384,10 @@ def run_ours(args):
                     "peak_gbs": peaks["hbm_gbs"], "frac": value / world * ALG_BYTES_PER_WINDOW / 1e9 / peaks["hbm_gbs"],
                     "note": "path is compute/latency bound (AI ~ 12 kFLOP/B); HBM fraction is <1 % by construction"},
             "stage_ms": stage_ms,
+            "coalesced": {"windows_per_pass": big, "windows_per_s_per_gpu": big / (big_total * 1e-3), "ms_per_pass": big_total,
+                          "stage_ms": big_ms, "kernels": big_kernels,
+                          "note": "device-resident, one stream, consecutive steps fused into one pass (what predict_host does); "
+                                  "TFLOP/s are algorithmic fp32 FLOPs: the tensor kernels spend 3 tf32 MMAs per product"},
         }
         if world == 1 and not args.no_cpu_baseline:
             wps, cores, sample = cpu_baseline_bounded(15.0, batch)
@@ -374,6 +409,7 @@ def main():
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--pool-batches", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--coalesce", type=int, default=2368, help="windows in the coalesced device pass (extra fields)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,7 +30,7 @@ HIDDEN_SIZE = 128
 NUM_LAYERS = 3
 
 READS, COLS, CLASSES = 200, 90, 5
-MAX_CHUNK = 1024          # windows per internal chunk (bounds scratch: 0.66 MB / window)
+MAX_CHUNK = 2368          # windows per internal chunk = 148 SMs x 16 (bounds scratch: 0.66 MB / window)
 
 
 def gru_init(gru):

@@ -98,7 +98,15 @@ __host__ __device__ constexpr int pk_wtc(int l) {
 constexpr int RTC_W = G3 * HID;                  // 49 152
 constexpr int RTC_DIR = 2 * RTC_W + HID;         // floats per direction
 __host__ __device__ constexpr int pk_rtc(int l, int d) { return pk_wtc(LAYERS) + (l * 2 + d) * RTC_DIR; }
-constexpr int PK_TOTAL = pk_rtc(LAYERS, 0);
+// W_ih images for proj_tc2.cu: [n_tile][k_block of 16][hi|lo][256 rows x 16 floats], 64-byte swizzle
+constexpr int T2_IMG = 256 * 16;                 // floats in one hi (or lo) image: 16 KB
+__host__ __device__ constexpr int pk_wt2_size(int l) { return (GI_N / 256) * (gru_inp(l) / 16) * 2 * T2_IMG; }
+__host__ __device__ constexpr int pk_wt2(int l) {
+    int off = pk_rtc(LAYERS, 0);
+    for (int i = 0; i < l; ++i) off += pk_wt2_size(i);
+    return off;
+}
+constexpr int PK_TOTAL = pk_wt2(LAYERS);
 
 // ---- workspace per window (floats) ------------------------------------------------------------
 constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
@@ -123,6 +131,9 @@ cudaError_t launch_proj(const float* A, int K, const float* W, const float* bias
 cudaError_t launch_proj_tc(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
                            cudaStream_t s);
 cudaError_t proj_tc_setup();
+cudaError_t launch_proj_tc2(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
+                            cudaStream_t s);
+cudaError_t proj_tc2_setup();
 cudaError_t launch_rec_tc(const float* gi, const float* whi_d0, const float* wlo_d0, size_t dir_stride,
                           const float* bhn_d0, float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t rec_tc_setup();

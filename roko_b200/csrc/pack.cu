@@ -49,6 +49,30 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) 
     }
     if (p < PK_B4) { int i = p - PK_W4; return i < CLASSES * OUT_W ? raw[RAW_W4 + i] : 0.f; }
     if (p < pk_wtc(0)) { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
+    if (p >= pk_wt2(0)) {      // tf32 hi/lo images of W_ih, 64-byte swizzle, 16-float k-blocks (proj_tc2.cu)
+        int l = 0;
+        while (l + 1 < LAYERS && p >= pk_wt2(l + 1)) ++l;
+        const int kin = gru_in(l), kblocks = gru_inp(l) / 16;
+        int i = p - pk_wt2(l);
+        const int ntile = i / (kblocks * 2 * T2_IMG);
+        i %= kblocks * 2 * T2_IMG;
+        const int kb = i / (2 * T2_IMG);
+        i %= 2 * T2_IMG;
+        const int half = i / T2_IMG;
+        const int ob = (i % T2_IMG) * 4;                 // byte offset inside the 16 KB image
+        const int rgrp = ob / 512, within = ob % 512;
+        const int r8 = within / 64, pchunk = (within % 64) / 16, w4 = (within % 16) / 4;
+        const int r = rgrp * 8 + r8;
+        const int kk = ((pchunk ^ ((r8 >> 1) & 3)) * 4) + w4;      // undo the 64B swizzle
+        const int k = kb * 16 + kk;
+        const int n = ntile * 256 + r;
+        const int d = n / G3, j = (n % G3) / 3, g = (n % G3) % 3;
+        const float v = k < kin ? raw[raw_wih(l, d) + (g * HID + j) * kin + k] : 0.f;
+        unsigned hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        const float hi = __uint_as_float(hb);
+        return half == 0 ? hi : v - hi;
+    }
     if (p >= pk_rtc(0, 0)) {   // tensor-core recurrence operands (rec_tc.cu)
         int i = p - pk_rtc(0, 0);
         const int ld = i / RTC_DIR, l = ld / 2, d = ld % 2;

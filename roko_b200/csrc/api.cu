@@ -49,8 +49,8 @@ struct roko_b200_model {
     float* raw_stage = nullptr;
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
-    int use_tc = 2;                 // projection: 2 = tcgen05 256x256 tile (proj_tc2.cu), 1 = 128x256 tile (ROKO_B200_PROJ=tc1),
-                                    // 0 = FFMA SGEMM (ROKO_B200_PROJ=ffma)
+    int use_tc = 3;                 // projection: 3 = persistent tcgen05, double-buffered accumulators (proj_tc3.cu, default);
+                                    // ROKO_B200_PROJ=tc2 -> 256x256 tile, tc1 -> 128x256 tile, ffma -> FFMA SGEMM
     int superbatch = 2368;          // windows per device pass of infer_host (148 SMs x 16; ROKO_B200_SUPERBATCH)
     int rec_tc_min = 256;           // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never)
     FrontConst fc;
@@ -96,7 +96,9 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
         float* outs[3] = {h0, h1, h0};
         for (int l = 0; l < LAYERS; ++l) {
             if (ev) CU(cudaEventRecord(ev[1 + 2 * l], s));
-            if (m->use_tc == 2)
+            if (m->use_tc == 3)
+                CU(launch_proj_tc3(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, m->num_sms, s));
+            else if (m->use_tc == 2)
                 CU(launch_proj_tc2(in, gru_inp(l), pk + pk_wt2(l), pk + pk_bgi(l), gi, rows, s));
             else if (m->use_tc)
                 CU(launch_proj_tc(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, s));
@@ -185,6 +187,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = rec_setup();
     if (e == cudaSuccess) e = proj_tc_setup();
     if (e == cudaSuccess) e = proj_tc2_setup();
+    if (e == cudaSuccess) e = proj_tc3_setup();
     if (e == cudaSuccess) e = rec_tc_setup();
     if (const char* rt = getenv("ROKO_B200_REC_TC_MIN")) m->rec_tc_min = atoi(rt);
     if (const char* sb = getenv("ROKO_B200_SUPERBATCH")) m->superbatch = atoi(sb) > 0 ? atoi(sb) : 1;
@@ -192,7 +195,8 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
         const char* pj = getenv("ROKO_B200_PROJ");
         if (pj && strcmp(pj, "ffma") == 0) m->use_tc = 0;
         else if (pj && strcmp(pj, "tc1") == 0) m->use_tc = 1;
-        else m->use_tc = 2;
+        else if (pj && strcmp(pj, "tc2") == 0) m->use_tc = 2;
+        else m->use_tc = 3;
     }
     if (e != cudaSuccess) {
         roko_b200_model_destroy(m);

@@ -134,6 +134,9 @@ cudaError_t proj_tc_setup();
 cudaError_t launch_proj_tc2(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
                             cudaStream_t s);
 cudaError_t proj_tc2_setup();
+cudaError_t launch_proj_tc3(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
+                            int num_sms, cudaStream_t s);
+cudaError_t proj_tc3_setup();
 cudaError_t launch_rec_tc(const float* gi, const float* whi_d0, const float* wlo_d0, size_t dir_stride,
                           const float* bhn_d0, float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t rec_tc_setup();

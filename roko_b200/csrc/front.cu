@@ -25,11 +25,18 @@
 
 namespace roko {
 
+#ifndef FR_NT_UNROLL_N
+#define FR_NT_UNROLL_N 1
+#endif
+#ifndef FR_STATIC_COLUMNS
+#define FR_DYNAMIC 1      // warps pull columns from a shared counter (evens out the 90-columns-over-16-warps tail)
+#endif
+constexpr int FR_NT_UNROLL = FR_NT_UNROLL_N;
 constexpr int FR_THREADS = 512;
 constexpr int FR_WARPS = FR_THREADS / 32;
 constexpr int LIST_LEN = 240;                 // 200 reads + up to 3 pads for each of 12 codes
 constexpr int JQ = FC1 / 4;                   // 25 gather lanes
-constexpr int EH = EMB / 2;                   // 25 a/g lanes, two embedding dims each
+constexpr int FC1P = 104;                     // fc1 width padded to 13 mma n-tiles
 
 struct FrontWarp {                            // private to one warp
     float m[FC1][NCODES];                     // 4 800 B
@@ -40,9 +47,15 @@ struct FrontWarp {                            // private to one warp
 struct FrontSmem {
     float w1t[W1T_ROWS * FC1];                // 80 400 B  [r][j], row 200 zero
     FrontWarp wp[FR_WARPS];                   // 80 896 B
-    alignas(16) float w2t[FC1][12];           //  4 800 B  [j] -> W2[0..9][j], b1[j], 0
+    // operands of the tensor-core a/g stage (tf32 hi / lo, zero padded):
+    alignas(16) float efrag[2][2][2][2][32][4];   //  8 192 B  E^T as mma A fragments [m-tile pair][m-tile][k-step][hi|lo][lane][reg]
+    alignas(16) float w2h[16][FC1P];              //  6 656 B  W2[k][j], k padded to 16, j to 104
+    alignas(16) float w2l[16][FC1P];              //  6 656 B
+    alignas(16) float b1p[FC1P];                  //    416 B
+    float b2p[16];
     alignas(16) uint8_t xs[2][READS * COLS];  // 36 000 B  double-buffered window, [read][col]
     alignas(8) unsigned long long xbar[2];    // TMA arrival barriers of the two window buffers
+    int next_col[2];                          // dynamic column scheduler, one counter per window buffer
 };
 
 __device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,8 +138,21 @@ __device__ __forceinline__ void build_m(const float* w1t, FrontWarp& W, int jq) 
     for (int c = 0; c < NCODES; ++c) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         const int i0 = W.start[c], i1 = W.start[c + 1];
+#ifdef FR_GATHER2
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        int i = i0;
+        if (i & 4) { if (i < i1) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i])); i += 4; }
+#pragma unroll 1
+        for (; i + 8 <= i1; i += 8) {
+            const uint2 q = *reinterpret_cast<const uint2*>(&W.list[i]);
+            add4(a, q.x); add4(b, q.y);
+        }
+        if (i < i1) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+#else
 #pragma unroll 1
         for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
+#endif
         acc[c] = a;
     }
     float4* m = reinterpret_cast<float4*>(&W.m[4 * jq][0]);
@@ -162,10 +188,25 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
         float4* dst = reinterpret_cast<float4*>(S.w1t);
         for (int i = tid; i < W1T_ROWS * FC1 / 4; i += FR_THREADS) dst[i] = src[i];
     }
-    for (int i = tid; i < FC1 * 12; i += FR_THREADS) {
-        const int j = i / 12, k = i % 12;
-        S.w2t[j][k] = k < FC2 ? P.W2[k * FC1 + j] : (k == FC2 ? P.b1[j] : 0.f);
+    auto tf32r = [](float v) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); return __uint_as_float(u); };
+    for (int i = tid; i < 2 * 2 * 2 * 2 * 32 * 4; i += FR_THREADS) {       // E^T in mma.m16n8k8 A-fragment order
+        const int q = i & 3, ln = (i >> 2) & 31, hl = (i >> 7) & 1, ks = (i >> 8) & 1, mtl = (i >> 9) & 1, mp = (i >> 10) & 1;
+        const int g = ln >> 2, t = ln & 3;
+        const int c = 8 * ks + t + ((q & 2) ? 4 : 0);                      // a0,a1: col t   a2,a3: col t+4
+        const int e = 16 * (2 * mp + mtl) + g + ((q & 1) ? 8 : 0);         // a0,a2: row g   a1,a3: row g+8
+        const float v = (c < NCODES && e < EMB) ? packed[PK_E + c * EMB + e] : 0.f;
+        const float hi = tf32r(v);
+        (&S.efrag[0][0][0][0][0][0])[i] = hl ? v - hi : hi;
     }
+    for (int i = tid; i < 16 * FC1P; i += FR_THREADS) {
+        const int k = i / FC1P, j = i % FC1P;
+        const float v = (k < FC2 && j < FC1) ? P.W2[k * FC1 + j] : 0.f;
+        const float hi = tf32r(v);
+        S.w2h[k][j] = hi;
+        S.w2l[k][j] = v - hi;
+    }
+    for (int i = tid; i < FC1P; i += FR_THREADS) S.b1p[i] = i < FC1 ? P.b1[i] : 0.f;
+    if (tid < 16) S.b2p[tid] = tid < FC2 ? P.b2[tid] : 0.f;
     __syncthreads();
     auto fetch_window = [&](int w, int buf) {      // one thread: TMA bulk copy of a whole window
         const uint32_t bar = fr_smem_u32(&S.xbar[buf]);
@@ -173,22 +214,17 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(fr_smem_u32(S.xs[buf])), "l"(x + (size_t)w * WIN_BYTES), "r"(WIN_BYTES), "r"(bar) : "memory");
     };
+    if (tid == 0) { S.next_col[0] = 0; S.next_col[1] = 0; }
     if (tid == 0 && (int)blockIdx.x < nwin) fetch_window(blockIdx.x, 0);
+    __syncthreads();
 
     FrontWarp& W = S.wp[warp];
-    // a/g stage: lane l < 25 owns embedding dims l and l + 25.  Lanes 25..31 run the same loop on a
-    // duplicate index and store nothing: keeping the loop in warp-uniform control flow lets the
-    // compiler index W2/b1 in the constant bank through the uniform datapath with a rolled loop
-    // (a fully unrolled body is 88 KB of code and thrashed the instruction cache: 2.1 stalled warps
-    // per issue on "no instruction").
-    const int el = lane < EH ? lane : lane - 8;
-    float E0[NCODES], E1[NCODES];
-#pragma unroll
-    for (int c = 0; c < NCODES; ++c) {
-        E0[c] = packed[PK_E + c * EMB + el];
-        E1[c] = packed[PK_E + c * EMB + el + EH];
-    }
-
+    // a/g stage on the tensor pipe (warp-level mma.sync m16n8k8 tf32, fp32-accurate 3xTF32 split):
+    //   stage A   a[e][j] = relu(b1[j] + sum_c E^T[e][c] M^T[c][j])      M = e (4 tiles of 16), N = j (13 tiles of 8), K = c (2 steps)
+    //   stage G   g[e][k] = relu(b2[k] + sum_j a[e][j] W2^T[j][k])       M = e, N = k (2 tiles of 8), K = j (one stage-A n-tile per step)
+    // The C fragment of stage A is reused as the A fragment of stage G by reading the contraction index in
+    // the order j = 8nt + {0,2,4,6,1,3,5,7}: C holds columns (2t, 2t+1), A wants columns (t, t+4).
+    const int fg = lane >> 2, ft = lane & 3;
     int it = 0;
     for (int w = blockIdx.x; w < nwin; w += gridDim.x, ++it) {
         const int xb = it & 1;
@@ -204,60 +240,105 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
         }
         // every warp is past the previous window (barrier at the bottom), so its buffer is free
         if (tid == 0 && w + (int)gridDim.x < nwin) fetch_window(w + gridDim.x, xb ^ 1);
+        if (tid == 0) S.next_col[xb ^ 1] = 0;      // the other buffer's counter is idle during this window
 
+#ifdef FR_DYNAMIC
+        for (;;) {
+            int p = 0;
+            if (lane == 0) p = atomicAdd(&S.next_col[xb], 1);
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (p >= COLS) break;
+#else
         for (int p = warp; p < COLS; p += FR_WARPS) {
+#endif
             sort_column(W, S.xs[xb], p, lane, status);
             __syncwarp();
             if (lane < JQ) build_m(S.w1t, W, lane);
             __syncwarp();
             float* urow = u + ((size_t)w * COLS + p) * IN0P;
-            {
-                float g0[FC2], g1[FC2];
+            auto split = [](float v, uint32_t& hi, uint32_t& lo) {
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+                lo = __float_as_uint(v - __uint_as_float(hi));
+            };
+            auto mma = [](float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+            };
+#pragma unroll 1
+            for (int mp = 0; mp < 2; ++mp) {                       // two passes of two 16-row tiles of e
+                uint32_t eh[2][2][4], el[2][2][4];
 #pragma unroll
-                for (int k = 0; k < FC2; ++k) g0[k] = g1[k] = P.b2[k];
-                const float4* mrow = reinterpret_cast<const float4*>(&W.m[0][0]);
-                const float4* wrow = reinterpret_cast<const float4*>(&S.w2t[0][0]);
-#pragma unroll 4
-                for (int j = 0; j < FC1; ++j) {
-                    const float4 m0 = mrow[j * 3], m1 = mrow[j * 3 + 1], m2 = mrow[j * 3 + 2];
-                    const float4 w0 = wrow[j * 3], w1 = wrow[j * 3 + 1], w2 = wrow[j * 3 + 2];   // W2[0..9][j], b1[j]
-                    // two embedding dims share every load; per dim three independent 4-term chains
-                    float a0 = fmaf(m0.x, E0[0], w2.z), b0 = fmaf(m0.x, E1[0], w2.z);
-                    float a1 = m1.x * E0[4], b1 = m1.x * E1[4];
-                    float a2 = m2.x * E0[8], b2 = m2.x * E1[8];
-                    a0 = fmaf(m0.y, E0[1], a0); b0 = fmaf(m0.y, E1[1], b0);
-                    a1 = fmaf(m1.y, E0[5], a1); b1 = fmaf(m1.y, E1[5], b1);
-                    a2 = fmaf(m2.y, E0[9], a2); b2 = fmaf(m2.y, E1[9], b2);
-                    a0 = fmaf(m0.z, E0[2], a0); b0 = fmaf(m0.z, E1[2], b0);
-                    a1 = fmaf(m1.z, E0[6], a1); b1 = fmaf(m1.z, E1[6], b1);
-                    a2 = fmaf(m2.z, E0[10], a2); b2 = fmaf(m2.z, E1[10], b2);
-                    a0 = fmaf(m0.w, E0[3], a0); b0 = fmaf(m0.w, E1[3], b0);
-                    a1 = fmaf(m1.w, E0[7], a1); b1 = fmaf(m1.w, E1[7], b1);
-                    a2 = fmaf(m2.w, E0[11], a2); b2 = fmaf(m2.w, E1[11], b2);
-                    const float a = fmaxf(a0 + (a1 + a2), 0.f), b = fmaxf(b0 + (b1 + b2), 0.f);
-                    g0[0] = fmaf(w0.x, a, g0[0]); g1[0] = fmaf(w0.x, b, g1[0]);
-                    g0[1] = fmaf(w0.y, a, g0[1]); g1[1] = fmaf(w0.y, b, g1[1]);
-                    g0[2] = fmaf(w0.z, a, g0[2]); g1[2] = fmaf(w0.z, b, g1[2]);
-                    g0[3] = fmaf(w0.w, a, g0[3]); g1[3] = fmaf(w0.w, b, g1[3]);
-                    g0[4] = fmaf(w1.x, a, g0[4]); g1[4] = fmaf(w1.x, b, g1[4]);
-                    g0[5] = fmaf(w1.y, a, g0[5]); g1[5] = fmaf(w1.y, b, g1[5]);
-                    g0[6] = fmaf(w1.z, a, g0[6]); g1[6] = fmaf(w1.z, b, g1[6]);
-                    g0[7] = fmaf(w1.w, a, g0[7]); g1[7] = fmaf(w1.w, b, g1[7]);
-                    g0[8] = fmaf(w2.x, a, g0[8]); g1[8] = fmaf(w2.x, b, g1[8]);
-                    g0[9] = fmaf(w2.y, a, g0[9]); g1[9] = fmaf(w2.y, b, g1[9]);
-                }
-                if (lane < EH) {
-                    float2* d0 = reinterpret_cast<float2*>(urow + lane * FC2);
-                    float2* d1 = reinterpret_cast<float2*>(urow + (lane + EH) * FC2);
+                for (int mtl = 0; mtl < 2; ++mtl)
 #pragma unroll
-                    for (int k = 0; k < FC2; k += 2) {
-                        d0[k / 2] = make_float2(fmaxf(g0[k], 0.f), fmaxf(g0[k + 1], 0.f));
-                        d1[k / 2] = make_float2(fmaxf(g1[k], 0.f), fmaxf(g1[k + 1], 0.f));
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint4 h4 = *reinterpret_cast<const uint4*>(&S.efrag[mp][mtl][ks][0][lane][0]);
+                        const uint4 l4 = *reinterpret_cast<const uint4*>(&S.efrag[mp][mtl][ks][1][lane][0]);
+                        eh[mtl][ks][0] = h4.x; eh[mtl][ks][1] = h4.y; eh[mtl][ks][2] = h4.z; eh[mtl][ks][3] = h4.w;
+                        el[mtl][ks][0] = l4.x; el[mtl][ks][1] = l4.y; el[mtl][ks][2] = l4.z; el[mtl][ks][3] = l4.w;
                     }
-                } else if (lane < EH + 3) {                        // zero the k-padding of the row
-                    reinterpret_cast<float4*>(urow + IN0)[lane - EH] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float gacc[2][2][4];
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt) {
+                    const float bx = S.b2p[8 * kt + 2 * ft], by = S.b2p[8 * kt + 2 * ft + 1];
+#pragma unroll
+                    for (int mtl = 0; mtl < 2; ++mtl) {
+                        gacc[mtl][kt][0] = bx; gacc[mtl][kt][1] = by; gacc[mtl][kt][2] = bx; gacc[mtl][kt][3] = by;
+                    }
                 }
+#pragma unroll FR_NT_UNROLL
+                for (int nt = 0; nt < FC1P / 8; ++nt) {
+                    // B fragments of stage A: M^T[c][j], j = 8nt + g, c = t, t+4, t+8 (c >= 12 is zero padding)
+                    const int jr = 8 * nt + fg;
+                    const bool jv = jr < FC1;
+                    uint32_t m0h, m0l, m4h, m4l, m8h, m8l;
+                    split(jv ? W.m[jr][ft] : 0.f, m0h, m0l);
+                    split(jv ? W.m[jr][ft + 4] : 0.f, m4h, m4l);
+                    split(jv ? W.m[jr][ft + 8] : 0.f, m8h, m8l);
+                    const float2 b1v = *reinterpret_cast<const float2*>(&S.b1p[8 * nt + 2 * ft]);
+                    // B fragments of stage G: W2[k = 8kt + g][j = 8nt + 2t, 2t + 1]
+                    uint2 wh[2], wl[2];
+#pragma unroll
+                    for (int kt = 0; kt < 2; ++kt) {
+                        wh[kt] = *reinterpret_cast<const uint2*>(&S.w2h[8 * kt + fg][8 * nt + 2 * ft]);
+                        wl[kt] = *reinterpret_cast<const uint2*>(&S.w2l[8 * kt + fg][8 * nt + 2 * ft]);
+                    }
+#pragma unroll
+                    for (int mtl = 0; mtl < 2; ++mtl) {
+                        float c[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma(c, el[mtl][0], m0h, m4h); mma(c, eh[mtl][0], m0l, m4l); mma(c, eh[mtl][0], m0h, m4h);
+                        mma(c, el[mtl][1], m8h, 0u);  mma(c, eh[mtl][1], m8l, 0u);  mma(c, eh[mtl][1], m8h, 0u);
+                        // c0:(g, 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)  ->  A of stage G: a0:(g, t) a1:(g+8, t) a2:(g, t+4) a3:(g+8, t+4)
+                        uint32_t ah[4], al[4];
+                        split(fmaxf(c[0] + b1v.x, 0.f), ah[0], al[0]);
+                        split(fmaxf(c[2] + b1v.x, 0.f), ah[1], al[1]);
+                        split(fmaxf(c[1] + b1v.y, 0.f), ah[2], al[2]);
+                        split(fmaxf(c[3] + b1v.y, 0.f), ah[3], al[3]);
+#pragma unroll
+                        for (int kt = 0; kt < 2; ++kt) {
+                            mma(gacc[mtl][kt], al, wh[kt].x, wh[kt].y);
+                            mma(gacc[mtl][kt], ah, wl[kt].x, wl[kt].y);
+                            mma(gacc[mtl][kt], ah, wh[kt].x, wh[kt].y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int mtl = 0; mtl < 2; ++mtl)
+#pragma unroll
+                    for (int kt = 0; kt < 2; ++kt) {
+                        const int e = 16 * (2 * mp + mtl) + fg, k = 8 * kt + 2 * ft;
+                        if (k < FC2) {
+                            if (e < EMB)
+                                *reinterpret_cast<float2*>(urow + e * FC2 + k) =
+                                    make_float2(fmaxf(gacc[mtl][kt][0], 0.f), fmaxf(gacc[mtl][kt][1], 0.f));
+                            if (e + 8 < EMB)
+                                *reinterpret_cast<float2*>(urow + (e + 8) * FC2 + k) =
+                                    make_float2(fmaxf(gacc[mtl][kt][2], 0.f), fmaxf(gacc[mtl][kt][3], 0.f));
+                        }
+                    }
             }
+            if (lane < (IN0P - IN0) / 4)                               // zero the k-padding of the row
+                reinterpret_cast<float4*>(urow + IN0)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();                                          // M slab is reused by the next column
         }
         __syncthreads();                                           // window done: its xs buffer may be refilled

@@ -73,6 +73,15 @@ int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, f
 int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_windows, int batch,
                          uint8_t* labels_host, float* logits_host);
 
+/* Scheduling knobs (no effect on results beyond fp32 rounding order):
+ *   "rec_tc_min"  chunks of at least this many windows run the recurrence on tcgen05 (default 256; 0 = never).
+ *                 Below it the register-resident FFMA recurrence has the lower latency; the tensor-core
+ *                 recurrence occupies 1/16 of the SMs per 128 windows and wins when several batches are in
+ *                 flight on different streams.
+ *   "superbatch"  windows per device pass of roko_b200_infer_host (default 2368)
+ *   "proj"        projection kernel: 3 persistent tcgen05 (default), 2 / 1 other tile shapes, 0 FFMA SGEMM */
+int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long value);
+
 /* Synchronises the device and reports sticky input errors seen by earlier forwards
  * (bit 0: code outside 0..11), then clears them.  Returns ROKO_B200_ECODES if any were set. */
 int roko_b200_model_check(roko_b200_model* m);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "roko_b200_infer_host": (ctypes.c_int, [c_model_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_void_p]),
     "roko_b200_model_check": (ctypes.c_int, [c_model_p]),
+    "roko_b200_model_set_option": (ctypes.c_int, [c_model_p, ctypes.c_char_p, ctypes.c_longlong]),
     "roko_b200_forward_taps": (ctypes.c_int, [c_model_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 7
                                + [ctypes.c_size_t, ctypes.c_void_p]),
     "roko_b200_forward_timed": (ctypes.c_int, [c_model_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,

@@ -358,6 +358,14 @@ int roko_b200_measure_fp32_peak(int device, double* tflops) {
     return ROKO_B200_OK;
 }
 
+int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long value) {
+    if (!m || !name) return fail(ROKO_B200_EARG, "model / name is NULL%s%s");
+    if (strcmp(name, "rec_tc_min") == 0) { m->rec_tc_min = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "superbatch") == 0) { if (value < 1) return fail(ROKO_B200_EARG, "superbatch < 1%s%s"); m->superbatch = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "proj") == 0) { if (value < 0 || value > 3) return fail(ROKO_B200_EARG, "proj must be 0..3%s%s"); m->use_tc = (int)value; return ROKO_B200_OK; }
+    return fail(ROKO_B200_EARG, "unknown option '%s'%s", name);
+}
+
 int roko_b200_model_check(roko_b200_model* m) {
     if (!m) return fail(ROKO_B200_EARG, "model is NULL%s%s");
     DeviceGuard g(m->device);

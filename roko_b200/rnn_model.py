@@ -213,6 +213,12 @@ class RNN(nn.Module):
         torch.cuda.current_stream(idx).synchronize()
         return t
 
+    def set_option(self, name, value, device=None):
+        """Scheduling knobs of the C library (see include/roko_b200.h): rec_tc_min, superbatch, proj."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        h = self._handle(dev)
+        _cabi.check(h.lib.roko_b200_model_set_option(h.ptr, name.encode(), int(value)))
+
     def check_codes(self):
         """Synchronise and raise IndexError if an earlier forward saw a code outside 0..11."""
         for h in self._handles.values():

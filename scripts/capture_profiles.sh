@@ -11,4 +11,7 @@ for spec in "front_kernel 128 1" "proj_tc3_kernel 128 3" "rec_kernel 128 3" "hea
     $T ncu --set full --clock-control none --import-source on -k regex:$1 -s $3 -c 2 \
         -o gpurun_out/final_${1}_b$2 python scripts/profile_target.py $2 3 > /dev/null 2>&1
 done
+# the tensor-core recurrence at one 128-window batch (the bench's throughput configuration)
+ROKO_B200_REC_TC_MIN=128 $T ncu --set full --clock-control none --import-source on -k regex:rec_tc_kernel -s 3 -c 2 \
+    -o gpurun_out/final_rec_tc_kernel_b128 python scripts/profile_target.py 128 3 > /dev/null 2>&1
 ls -la gpurun_out | grep final_

@@ -91,6 +91,12 @@ class RNN(nn.Module):
         self.fc4 = nn.Linear(2 * hidden_size, CLASSES)
         self._handles = {}
 
+    # the C handles (device pointers) are a derived cache: never copied or pickled with the module
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}
+        return state
+
     # ---- packed-weight cache ------------------------------------------------------------------
     def _ordered_params(self):
         sd = dict(self.named_parameters())

@@ -90,6 +90,22 @@ def test_no_cpu_fallback(seed1_state, golden):
         m.predict(torch.zeros((1, 200, 30), dtype=torch.uint8))          # wrong geometry
 
 
+def test_module_copies_do_not_share_device_handles(seed1_state):
+    import copy, pickle
+    import roko_b200.rnn_model as rm
+    m = rm.RNN(500, 128, 3)
+    m.load_state_dict(seed1_state)
+    m._handles["fake"] = object()                       # stands in for a live C handle
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone._handles == {}
+        assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
+
+
+def test_set_option_rejects_unknown_names(lib):
+    from roko_b200 import _cabi
+    assert lib.roko_b200_model_set_option(None, b"rec_tc_min", 128) == _cabi.EARG
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from roko_b200 import _cabi
     monkeypatch.setattr(_cabi, "_lib", None)

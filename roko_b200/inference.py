@@ -14,6 +14,11 @@ Reference behaviour mirrored (file:line in /root/reference/roko/inference.py):
     prefix and suffix                                                 :129-151
   * FASTA via ``SeqIO.write`` of ``SeqRecord(seq, id=contig)``        :149-154
 
+Two drivers share the dataset / vote / stitch code: ``infer`` keeps the reference's per-batch loop
+(DataLoader of single windows, one model call per batch); ``infer_fast`` (the CLI default) reads
+``examples[i:i+n]`` slabs per group, pushes them through ``RNN.predict_host`` (pinned staging, batches
+coalesced into device passes) and votes with dense scatter-adds on the GPU.  Both produce the same FASTA.
+
 Differences, all on the host side of the boundary: windows stay uint8 end to end (the reference
 widens to int64 before the copy, :113); labels come back as uint8 from the fused argmax; the
 per-position Python ``Counter`` loop (:119-124, ~44 ms per 128-window batch) is a vectorised
@@ -188,6 +193,109 @@ def infer(data, model_path, out, workers=0, batch_size=128, h5=None, device=None
     return records
 
 
+class DenseVoteTable:
+    """Same ``Counter`` semantics as ``VoteTable`` but dense and in torch (CPU or CUDA tensors):
+    per contig ``counts[(rpos * 4 + ins), label]`` by scatter-add and the sequence number of each label's
+    first vote by scatter-amin; sized from the contig length (slots for rpos 0..len-1, ins 0..3)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.tables = {}
+        self.seq = 0
+
+    def add(self, contig, contig_len, pos, labels):
+        """pos (n,2) int64 tensor [(rpos, ins)], labels (n,) uint8 tensor, in window/position order."""
+        t = self.tables.get(contig)
+        if t is None:
+            slots = int(contig_len) * (MAX_INS + 1)
+            t = self.tables[contig] = {
+                "counts": torch.zeros(slots * N_LABELS, dtype=torch.int32, device=self.device),
+                "first": torch.full((slots * N_LABELS,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=self.device)}
+        pos = pos.to(self.device, torch.int64)
+        idx = (pos[:, 0] * (MAX_INS + 1) + pos[:, 1]) * N_LABELS + labels.to(self.device, torch.int64)
+        t["counts"].scatter_add_(0, idx, torch.ones_like(idx, dtype=torch.int32))
+        order = torch.arange(self.seq, self.seq + idx.numel(), dtype=torch.int64, device=self.device)
+        t["first"].scatter_reduce_(0, idx, order, reduce="amin", include_self=True)
+        self.seq += idx.numel()
+
+    def consensus(self, contig):
+        t = self.tables[contig]
+        counts = t["counts"].view(-1, N_LABELS)
+        first = t["first"].view(-1, N_LABELS)
+        best = counts.max(dim=1, keepdim=True).values
+        voted = torch.nonzero(best[:, 0] > 0)[:, 0]
+        cand = torch.where(counts[voted] == best[voted], first[voted], torch.full_like(first[voted], torch.iinfo(torch.int64).max))
+        winner = cand.argmin(dim=1)
+        keys = voted.cpu().numpy()
+        return np.stack([keys // (MAX_INS + 1), keys % (MAX_INS + 1)], axis=1), winner.cpu().numpy()
+
+
+class _SlabDataset(Dataset):
+    """One item = up to ``chunk`` consecutive windows of one group, read as slabs (row f3 of SURVEY.md 8f)."""
+
+    def __init__(self, path, chunk, h5=None):
+        self.path, self.chunk, self._h5mod, self.fd = path, chunk, h5, None
+        self.items, self.contigs = [], {}
+        fd = self._open()
+        try:
+            for g in fd.keys():
+                if g == "contigs":
+                    continue
+                n = int(fd[g].attrs["size"])
+                self.items.extend((g, a, min(a + chunk, n)) for a in range(0, n, chunk))
+            for k in fd["contigs"]:
+                grp = fd["contigs"][k]
+                self.contigs[str(k)] = (grp.attrs["seq"], grp.attrs["len"])
+        finally:
+            fd.close()
+
+    def _open(self):
+        return (self._h5mod or _h5()).File(self.path, "r")
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        if self.fd is None:
+            self.fd = self._open()
+        g, a, b = self.items[i]
+        grp = self.fd[g]
+        return (grp.attrs["contig"], torch.from_numpy(np.ascontiguousarray(grp["positions"][a:b])),
+                torch.from_numpy(np.ascontiguousarray(grp["examples"][a:b])))
+
+
+def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device=None, chunk=8192):
+    """Throughput driver: slab reads -> predict_host (coalesced device passes) -> dense GPU vote -> stitch."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("roko_b200.inference needs a CUDA (sm_100a) device: the model path has no CPU fallback")
+    device = torch.device(device or "cuda:0")
+    model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)
+    model.load_state_dict(torch.load(model_path, map_location=device))
+    model.eval()
+
+    dataset = _SlabDataset(data, chunk, h5=h5)
+    loader = DataLoader(dataset, batch_size=None, shuffle=False, num_workers=workers)
+    votes = DenseVoteTable(device)
+    x_pin = torch.empty((chunk, 200, 90), dtype=torch.uint8).pin_memory()
+    y_pin = torch.empty((chunk, 90), dtype=torch.uint8).pin_memory()
+    print("Inference started")
+    done = 0
+    for contig, pos, x in loader:
+        n = x.shape[0]
+        x_pin[:n].copy_(x)
+        model.predict_host(x_pin[:n], batch=batch_size, out=y_pin[:n], device=device)
+        votes.add(contig, dataset.contigs[contig][1], pos.reshape(-1, 2), y_pin[:n].reshape(-1))
+        done += n
+        if (done // batch_size) % 100 == 0:
+            print(f"{done // batch_size} batches processed")
+    records = []
+    for contig in votes.tables:
+        positions, winners = votes.consensus(contig)
+        records.append((contig, stitch(dataset.contigs[contig][0], positions, winners)))
+    write_fasta(records, out)
+    return records
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("data", type=str)
@@ -195,8 +303,9 @@ def main():
     parser.add_argument("out", type=str)
     parser.add_argument("--t", type=int, default=0)
     parser.add_argument("--b", type=int, default=128)
+    parser.add_argument("--per-batch", action="store_true", help="the reference's per-batch loop instead of slab reads")
     args = parser.parse_args()
-    infer(args.data, args.model, args.out, args.t, args.b)
+    (infer if args.per_batch else infer_fast)(args.data, args.model, args.out, args.t, args.b)
 
 
 if __name__ == "__main__":

@@ -67,6 +67,22 @@ def test_vote_table_matches_counter_semantics(seed):
     assert mine == reference_vote_and_stitch(contigs, batches)
 
 
+@pytest.mark.parametrize("seed", [3, 4])
+def test_dense_vote_table_matches_counter_semantics(seed):
+    import torch
+    rng = np.random.default_rng(seed)
+    contigs = {"ctgA": "".join(rng.choice(list("ACGT"), 500))}
+    pos = make_windows(rng, 500, 12)
+    Y = rng.integers(0, 5, size=pos.shape[:2]).astype(np.uint8)
+    batches, votes = [], inf.DenseVoteTable("cpu")
+    for b0 in range(0, len(pos), 5):
+        sl = slice(b0, b0 + 5)
+        batches.append((["ctgA"] * len(pos[sl]), pos[sl], Y[sl]))
+        votes.add("ctgA", 500, torch.from_numpy(pos[sl].reshape(-1, 2)), torch.from_numpy(Y[sl].reshape(-1)))
+    p, w = votes.consensus("ctgA")
+    assert [("ctgA", inf.stitch(contigs["ctgA"], p, w))] == reference_vote_and_stitch(contigs, batches)
+
+
 def test_fasta_writer_format(tmp_path):
     path = tmp_path / "o.fasta"
     inf.write_fasta([("c1", "A" * 130), ("c2", "ACGT")], str(path))
@@ -103,3 +119,7 @@ def test_infer_end_to_end_on_gpu(tmp_path, seed1_state, seed1_weights):
     batches = [(["ctg1"] * len(pos[i:i + 7]), pos[i:i + 7], labels[i:i + 7]) for i in range(0, len(pos), 7)]
     assert recs == reference_vote_and_stitch({"ctg1": draft}, batches)
     assert (tmp_path / "out.fasta").read_text().startswith(">ctg1 <unknown description>\n")
+    # the slab / predict_host / dense-vote driver gives the same consensus (votes arrive group by group, in order)
+    fast = inf.infer_fast("mem://e2e", str(pth), str(tmp_path / "out_fast.fasta"), workers=0, batch_size=7, h5=fake_h5, chunk=6)
+    assert fast == recs
+    assert (tmp_path / "out_fast.fasta").read_text() == (tmp_path / "out.fasta").read_text()

@@ -16,22 +16,19 @@
 //             W1T row
 //   gather    lane = 4 consecutive j (25 lanes): sum W1T rows over each list (LDS.128 + 4 FADD per
 //             read) -> the column's M (100 x 12) in the warp's private shared-memory slab
-//   a, g      lane = two embedding dims (e, e+25): a and g entirely in registers; W2/b1/b2 are
-//             constant-bank operands (kernel parameters), M rows are warp-broadcast LDS.128
+//   a, g      two chained warp-level tensor-core GEMMs (mma.sync m16n8k8 tf32, 3xTF32 split):
+//             a = relu(b1 + E^T M^T) feeds g = relu(b2 + a W2^T) without leaving registers -- the C
+//             fragment of the first is the A fragment of the second under a permuted contraction order
 // The 16 warps of a CTA drift apart, so the latency-bound gather of some warps overlaps the
-// FFMA-bound a/g stage of others without any block-level barrier (an earlier producer/consumer
+// tensor-pipe a/g stage of others without any block-level barrier (an earlier producer/consumer
 // split on named barriers serialised: 0.10 + 0.10 = 0.21 ms per 128 windows).
 #include "common.cuh"
 
 namespace roko {
 
-#ifndef FR_NT_UNROLL_N
-#define FR_NT_UNROLL_N 1
-#endif
 #ifndef FR_STATIC_COLUMNS
 #define FR_DYNAMIC 1      // warps pull columns from a shared counter (evens out the 90-columns-over-16-warps tail)
 #endif
-constexpr int FR_NT_UNROLL = FR_NT_UNROLL_N;
 constexpr int FR_THREADS = 512;
 constexpr int FR_WARPS = FR_THREADS / 32;
 constexpr int LIST_LEN = 240;                 // 200 reads + up to 3 pads for each of 12 codes
@@ -138,21 +135,8 @@ __device__ __forceinline__ void build_m(const float* w1t, FrontWarp& W, int jq) 
     for (int c = 0; c < NCODES; ++c) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         const int i0 = W.start[c], i1 = W.start[c + 1];
-#ifdef FR_GATHER2
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        int i = i0;
-        if (i & 4) { if (i < i1) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i])); i += 4; }
-#pragma unroll 1
-        for (; i + 8 <= i1; i += 8) {
-            const uint2 q = *reinterpret_cast<const uint2*>(&W.list[i]);
-            add4(a, q.x); add4(b, q.y);
-        }
-        if (i < i1) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-#else
 #pragma unroll 1
         for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
-#endif
         acc[c] = a;
     }
     float4* m = reinterpret_cast<float4*>(&W.m[4 * jq][0]);
@@ -286,7 +270,7 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                         gacc[mtl][kt][0] = bx; gacc[mtl][kt][1] = by; gacc[mtl][kt][2] = bx; gacc[mtl][kt][3] = by;
                     }
                 }
-#pragma unroll FR_NT_UNROLL
+#pragma unroll 1
                 for (int nt = 0; nt < FC1P / 8; ++nt) {
                     // B fragments of stage A: M^T[c][j], j = 8nt + g, c = t, t+4, t+8 (c >= 12 is zero padding)
                     const int jr = 8 * nt + fg;

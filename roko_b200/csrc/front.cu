@@ -19,26 +19,28 @@
 //   a, g      two chained warp-level tensor-core GEMMs (mma.sync m16n8k8 tf32, 3xTF32 split):
 //             a = relu(b1 + E^T M^T) feeds g = relu(b2 + a W2^T) without leaving registers -- the C
 //             fragment of the first is the A fragment of the second under a permuted contraction order
-// The 16 warps of a CTA drift apart, so the latency-bound gather of some warps overlaps the
-// tensor-pipe a/g stage of others without any block-level barrier (an earlier producer/consumer
-// split on named barriers serialised: 0.10 + 0.10 = 0.21 ms per 128 windows).
+// Odd warps sort all their columns up front so the two halves of the CTA run out of phase.  Measured
+// on B200 (128 windows): sort+gather alone 0.076 ms, a/g alone 0.104 ms, together 0.151 ms -- the two
+// barely overlap because legacy mma.sync holds the sub-partition's issue port for ~8.5 cycles per
+// instruction (480 MAC/clk/SM, scripts/ubench/mma_rate.cu); the next step is to move a/g to tcgen05.
 #include "common.cuh"
 
 namespace roko {
 
-#ifndef FR_STATIC_COLUMNS
-#define FR_DYNAMIC 1      // warps pull columns from a shared counter (evens out the 90-columns-over-16-warps tail)
-#endif
 constexpr int FR_THREADS = 512;
 constexpr int FR_WARPS = FR_THREADS / 32;
 constexpr int LIST_LEN = 240;                 // 200 reads + up to 3 pads for each of 12 codes
 constexpr int JQ = FC1 / 4;                   // 25 gather lanes
 constexpr int FC1P = 104;                     // fc1 width padded to 13 mma n-tiles
 
-struct FrontWarp {                            // private to one warp
-    float m[FC1][NCODES];                     // 4 800 B
+constexpr int FR_MAXCOLS = (COLS + FR_WARPS - 1) / FR_WARPS;   // columns a warp owns per window (6)
+struct FrontList {
     alignas(16) uint8_t list[LIST_LEN];       //   240 B
     uint8_t start[16];
+};
+struct FrontWarp {                            // private to one warp
+    float m[FC1][NCODES];                     // 4 800 B
+    FrontList cols[FR_MAXCOLS];               // 1 536 B  sorted read lists of this warp's columns
 };
 
 struct FrontSmem {
@@ -50,9 +52,8 @@ struct FrontSmem {
     alignas(16) float w2l[16][FC1P];              //  6 656 B
     alignas(16) float b1p[FC1P];                  //    416 B
     float b2p[16];
-    alignas(16) uint8_t xs[2][READS * COLS];  // 36 000 B  double-buffered window, [read][col]
-    alignas(8) unsigned long long xbar[2];    // TMA arrival barriers of the two window buffers
-    int next_col[2];                          // dynamic column scheduler, one counter per window buffer
+    alignas(16) uint8_t xs[READS * COLS];     // 18 000 B  the window, [read][col] (single buffer: the per-warp lists took the space)
+    alignas(8) unsigned long long xbar;       // TMA arrival barrier of the window buffer
 };
 
 __device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,7 +67,7 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w0, uint32_t w1, uint32_t w
     return (w >> ((code & 3u) * 8u)) & 0xffu;
 }
 
-__device__ __forceinline__ void sort_column(FrontWarp& W, const uint8_t* xs, int p, int lane, int* status) {
+__device__ __forceinline__ void sort_column(FrontList& W, const uint8_t* xs, int p, int lane, int* status) {
     uint32_t codes[7];
     uint32_t h0 = 0, h1 = 0, h2 = 0;               // my histogram
     uint32_t rank[7];                              // rank of read i among my earlier reads of the same code
@@ -118,7 +119,7 @@ __device__ __forceinline__ void sort_column(FrontWarp& W, const uint8_t* xs, int
     }
 }
 
-__device__ __forceinline__ void build_m(const float* w1t, FrontWarp& W, int jq) {
+__device__ __forceinline__ void build_m(const float* w1t, const FrontList& W, float (*mslab)[NCODES], int jq) {
     const float4* w4 = reinterpret_cast<const float4*>(w1t);
     float4 acc[NCODES];
     auto add4 = [&](float4& a, uint32_t q) {       // four list entries -> four W1T rows
@@ -139,7 +140,7 @@ __device__ __forceinline__ void build_m(const float* w1t, FrontWarp& W, int jq) 
         for (int i = i0; i < i1; i += 4) add4(a, *reinterpret_cast<const uint32_t*>(&W.list[i]));
         acc[c] = a;
     }
-    float4* m = reinterpret_cast<float4*>(&W.m[4 * jq][0]);
+    float4* m = reinterpret_cast<float4*>(&mslab[4 * jq][0]);
     m[0] = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
     m[1] = make_float4(acc[4].x, acc[5].x, acc[6].x, acc[7].x);
     m[2] = make_float4(acc[8].x, acc[9].x, acc[10].x, acc[11].x);
@@ -163,8 +164,7 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     constexpr uint32_t WIN_BYTES = READS * COLS;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fr_smem_u32(&S.xbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fr_smem_u32(&S.xbar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fr_smem_u32(&S.xbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // W1T (with its zero row) stays resident for every window this CTA processes
@@ -192,14 +192,13 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     for (int i = tid; i < FC1P; i += FR_THREADS) S.b1p[i] = i < FC1 ? P.b1[i] : 0.f;
     if (tid < 16) S.b2p[tid] = tid < FC2 ? P.b2[tid] : 0.f;
     __syncthreads();
-    auto fetch_window = [&](int w, int buf) {      // one thread: TMA bulk copy of a whole window
-        const uint32_t bar = fr_smem_u32(&S.xbar[buf]);
+    auto fetch_window = [&](int w) {               // one thread: TMA bulk copy of a whole window
+        const uint32_t bar = fr_smem_u32(&S.xbar);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(WIN_BYTES) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(fr_smem_u32(S.xs[buf])), "l"(x + (size_t)w * WIN_BYTES), "r"(WIN_BYTES), "r"(bar) : "memory");
+                     ::"r"(fr_smem_u32(S.xs)), "l"(x + (size_t)w * WIN_BYTES), "r"(WIN_BYTES), "r"(bar) : "memory");
     };
-    if (tid == 0) { S.next_col[0] = 0; S.next_col[1] = 0; }
-    if (tid == 0 && (int)blockIdx.x < nwin) fetch_window(blockIdx.x, 0);
+    if (tid == 0 && (int)blockIdx.x < nwin) fetch_window(blockIdx.x);
     __syncthreads();
 
     FrontWarp& W = S.wp[warp];
@@ -211,9 +210,8 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     const int fg = lane >> 2, ft = lane & 3;
     int it = 0;
     for (int w = blockIdx.x; w < nwin; w += gridDim.x, ++it) {
-        const int xb = it & 1;
         {   // wait for this window's bytes
-            const uint32_t bar = fr_smem_u32(&S.xbar[xb]), parity = (it >> 1) & 1;
+            const uint32_t bar = fr_smem_u32(&S.xbar), parity = it & 1;
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "W_%=:\n\t"
@@ -222,22 +220,19 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                 "bra W_%=;\n\t"
                 "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
         }
-        // every warp is past the previous window (barrier at the bottom), so its buffer is free
-        if (tid == 0 && w + (int)gridDim.x < nwin) fetch_window(w + gridDim.x, xb ^ 1);
-        if (tid == 0) S.next_col[xb ^ 1] = 0;      // the other buffer's counter is idle during this window
 
-#ifdef FR_DYNAMIC
-        for (;;) {
-            int p = 0;
-            if (lane == 0) p = atomicAdd(&S.next_col[xb], 1);
-            p = __shfl_sync(0xffffffffu, p, 0);
-            if (p >= COLS) break;
-#else
-        for (int p = warp; p < COLS; p += FR_WARPS) {
-#endif
-            sort_column(W, S.xs[xb], p, lane, status);
+        // Static column ownership (p = warp, warp + 16, ...).  The two halves of the CTA run out of phase on
+        // purpose: odd warps sort ALL their columns before the first gather, even warps sort each column
+        // just before it.  The gather is bound by shared-memory wavefronts and the a/g stage by the tensor
+        // pipe; with every warp in the same phase at the same time the two costs simply add
+        // (measured: 0.053 + 0.090 + sort 0.010 + fixed 0.014 = 0.159 ms per 128 windows).
+        const bool presort = warp & 1;
+        if (presort)
+            for (int ci = 0, p = warp; p < COLS; p += FR_WARPS, ++ci) sort_column(W.cols[ci], S.xs, p, lane, status);
+        for (int ci = 0, p = warp; p < COLS; p += FR_WARPS, ++ci) {
+            if (!presort) sort_column(W.cols[ci], S.xs, p, lane, status);
             __syncwarp();
-            if (lane < JQ) build_m(S.w1t, W, lane);
+            if (lane < JQ) build_m(S.w1t, W.cols[ci], W.m, lane);
             __syncwarp();
             float* urow = u + ((size_t)w * COLS + p) * IN0P;
             auto split = [](float v, uint32_t& hi, uint32_t& lo) {
@@ -325,7 +320,8 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                 reinterpret_cast<float4*>(urow + IN0)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();                                          // M slab is reused by the next column
         }
-        __syncthreads();                                           // window done: its xs buffer may be refilled
+        __syncthreads();                                           // every warp has sorted its columns: refill the buffer
+        if (tid == 0 && w + (int)gridDim.x < nwin) fetch_window(w + gridDim.x);
     }
 }
 

@@ -7,6 +7,8 @@
 //     epilogue cost as much as a K=256 main loop (0.35 of 0.61 ms at 2368 windows) while skipping a
 //     third of the MMAs or the whole operand feed changed the time by < 5 %.
 //   * warp roles: 0-3 A producers, 4 TMA W loader, 5 MMA issuer (+TMEM alloc), 6-9 epilogue.
+//   * the epilogue transposes each 32 x 32 block through shared memory so global stores are whole 128-byte
+//     row segments.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -18,7 +20,9 @@ constexpr int P3_STAGES = 2;
 constexpr int P3_A_IMG = TC_BM * TC_BK * 4;            // 16 KB
 constexpr int P3_W_IMG = TC_BN * TC_BK * 4;            // 32 KB
 constexpr int P3_STAGE = 2 * P3_A_IMG + 2 * P3_W_IMG;  // 96 KB
-constexpr int P3_SMEM = P3_STAGES * P3_STAGE + 1024 + 256;
+constexpr int P3_EPI_ROW = 36;                          // floats per staged row (144 B: 16-byte aligned, conflict free both ways)
+constexpr int P3_EPI_BYTES = 4 * 32 * P3_EPI_ROW * 4;   // one 32 x 32 staging tile per epilogue warp
+constexpr int P3_SMEM = P3_STAGES * P3_STAGE + 1024 + 256 + P3_EPI_BYTES;
 constexpr int P3_TMEM_COLS = 512;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -84,6 +88,7 @@ proj_tc3_kernel(const float* __restrict__ A, const float* __restrict__ wimg, con
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)p3_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P3_STAGES * P3_STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* epi_stage = reinterpret_cast<float*>(smem + P3_STAGES * P3_STAGE + 256);
     const uint32_t sbase = p3_smem_u32(smem);
     const uint32_t bar0 = p3_smem_u32(bars);
     // barriers: full_a[s] = s, full_w[s] = 2+s, empty[s] = 4+s, acc_full[b] = 6+b, acc_empty[b] = 8+b
@@ -208,10 +213,14 @@ proj_tc3_kernel(const float* __restrict__ A, const float* __restrict__ wimg, con
             const int m0 = (tile / 3) * TC_BM, n_tile = tile % 3;
             p3_mbar_wait(BAR(6 + buf), (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int m = m0 + q * 32 + lane;
+            // TMEM lane == tile row: this thread owns row q*32 + lane.  Rows are staged through a 32 x 32
+            // shared tile so that every global store instruction writes four whole 128-byte row segments
+            // (storing straight from the TMEM layout puts the 32 lanes of an instruction on 32 different rows,
+            // 16 bytes each: the epilogue then takes longer than the K=256 main loop it should hide behind).
             const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * TC_BN;
-            float* crow = C + (size_t)(m < M ? m : 0) * GI_N + n_tile * TC_BN;
+            float* T = epi_stage + (warp - 6) * 32 * P3_EPI_ROW;
             const float* brow = bias + n_tile * TC_BN;
+            const int rsub = lane >> 3, csub = (lane & 7) * 4;      // read-back role: 4 rows x 8 float4 per instruction
 #pragma unroll 1
             for (int c0 = 0; c0 < TC_BN; c0 += 32) {
                 uint32_t r[32];
@@ -225,18 +234,22 @@ proj_tc3_kernel(const float* __restrict__ A, const float* __restrict__ wimg, con
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr + (uint32_t)c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < M) {
 #pragma unroll
-                    for (int qq = 0; qq < 8; ++qq) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + qq * 4));
-                        float4 o;
-                        o.x = __uint_as_float(r[qq * 4 + 0]) + b.x;
-                        o.y = __uint_as_float(r[qq * 4 + 1]) + b.y;
-                        o.z = __uint_as_float(r[qq * 4 + 2]) + b.z;
-                        o.w = __uint_as_float(r[qq * 4 + 3]) + b.w;
-                        *reinterpret_cast<float4*>(crow + c0 + qq * 4) = o;
-                    }
+                for (int qq = 0; qq < 8; ++qq)                       // my row, 32 columns -> staging tile (row-wise STS.128)
+                    *reinterpret_cast<float4*>(T + lane * P3_EPI_ROW + qq * 4) =
+                        make_float4(__uint_as_float(r[qq * 4 + 0]), __uint_as_float(r[qq * 4 + 1]),
+                                    __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
+                __syncwarp();
+                const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + csub));
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {                     // rows 4*it .. 4*it+3, all 32 columns, coalesced
+                    const int rr = it * 4 + rsub;
+                    const int m = m0 + q * 32 + rr;
+                    float4 v = *reinterpret_cast<const float4*>(T + rr * P3_EPI_ROW + csub);
+                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    if (m < M) *reinterpret_cast<float4*>(C + (size_t)m * GI_N + n_tile * TC_BN + c0 + csub) = v;
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             p3_mbar_arrive(BAR(8 + buf));                          // accumulator may be overwritten

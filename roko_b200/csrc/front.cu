@@ -48,8 +48,9 @@ struct FrontSmem {
     FrontWarp wp[FR_WARPS];                   // 80 896 B
     // operands of the tensor-core a/g stage (tf32 hi / lo, zero padded):
     alignas(16) float efrag[2][2][2][2][32][4];   //  8 192 B  E^T as mma A fragments [m-tile pair][m-tile][k-step][hi|lo][lane][reg]
-    alignas(16) float w2h[16][FC1P];              //  6 656 B  W2[k][j], k padded to 16, j to 104
-    alignas(16) float w2l[16][FC1P];              //  6 656 B
+    alignas(16) float w2h[8][FC1P];               //  3 328 B  W2[k][j] for k = 0..7 (tf32 hi), j padded to 104
+    alignas(16) float w2l[8][FC1P];               //  3 328 B  (tf32 lo)
+    alignas(16) float w2f[2][FC1P];               //    832 B  W2[8][j], W2[9][j] in full fp32
     alignas(16) float b1p[FC1P];                  //    416 B
     float b2p[16];
     alignas(16) uint8_t xs[READS * COLS];     // 18 000 B  the window, [read][col] (single buffer: the per-warp lists took the space)
@@ -182,12 +183,16 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
         const float hi = tf32r(v);
         (&S.efrag[0][0][0][0][0][0])[i] = hl ? v - hi : hi;
     }
-    for (int i = tid; i < 16 * FC1P; i += FR_THREADS) {
+    for (int i = tid; i < FC2 * FC1P; i += FR_THREADS) {
         const int k = i / FC1P, j = i % FC1P;
-        const float v = (k < FC2 && j < FC1) ? P.W2[k * FC1 + j] : 0.f;
-        const float hi = tf32r(v);
-        S.w2h[k][j] = hi;
-        S.w2l[k][j] = v - hi;
+        const float v = j < FC1 ? P.W2[k * FC1 + j] : 0.f;
+        if (k < 8) {
+            const float hi = tf32r(v);
+            S.w2h[k][j] = hi;
+            S.w2l[k][j] = v - hi;
+        } else {
+            S.w2f[k - 8][j] = v;
+        }
     }
     for (int i = tid; i < FC1P; i += FR_THREADS) S.b1p[i] = i < FC1 ? P.b1[i] : 0.f;
     if (tid < 16) S.b2p[tid] = tid < FC2 ? P.b2[tid] : 0.f;
@@ -256,13 +261,16 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                         eh[mtl][ks][0] = h4.x; eh[mtl][ks][1] = h4.y; eh[mtl][ks][2] = h4.z; eh[mtl][ks][3] = h4.w;
                         el[mtl][ks][0] = l4.x; el[mtl][ks][1] = l4.y; el[mtl][ks][2] = l4.z; el[mtl][ks][3] = l4.w;
                     }
-                float gacc[2][2][4];
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
-                    const float bx = S.b2p[8 * kt + 2 * ft], by = S.b2p[8 * kt + 2 * ft + 1];
+                // k = 0..7 of stage G run on the tensor pipe; k = 8, 9 would need a second n-tile that is 3/4
+                // padding, so they are accumulated with plain FFMAs from the same a values (4 partial sums per
+                // tile, reduced over the 4 lanes of a row group at the end of the column)
+                float gacc[2][4], g89[2][4];
+                {
+                    const float bx = S.b2p[2 * ft], by = S.b2p[2 * ft + 1];
 #pragma unroll
                     for (int mtl = 0; mtl < 2; ++mtl) {
-                        gacc[mtl][kt][0] = bx; gacc[mtl][kt][1] = by; gacc[mtl][kt][2] = bx; gacc[mtl][kt][3] = by;
+                        gacc[mtl][0] = bx; gacc[mtl][1] = by; gacc[mtl][2] = bx; gacc[mtl][3] = by;
+                        g89[mtl][0] = g89[mtl][1] = g89[mtl][2] = g89[mtl][3] = 0.f;
                     }
                 }
 #pragma unroll 1
@@ -276,45 +284,52 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
                     split(jv ? W.m[jr][ft + 8] : 0.f, m8h, m8l);
                     const float2 b1v = *reinterpret_cast<const float2*>(&S.b1p[8 * nt + 2 * ft]);
                     // B fragments of stage G: W2[k = 8kt + g][j = 8nt + 2t, 2t + 1]
-                    uint2 wh[2], wl[2];
-#pragma unroll
-                    for (int kt = 0; kt < 2; ++kt) {
-                        wh[kt] = *reinterpret_cast<const uint2*>(&S.w2h[8 * kt + fg][8 * nt + 2 * ft]);
-                        wl[kt] = *reinterpret_cast<const uint2*>(&S.w2l[8 * kt + fg][8 * nt + 2 * ft]);
-                    }
+                    const uint2 wh = *reinterpret_cast<const uint2*>(&S.w2h[fg][8 * nt + 2 * ft]);
+                    const uint2 wl = *reinterpret_cast<const uint2*>(&S.w2l[fg][8 * nt + 2 * ft]);
+                    const float2 w8 = *reinterpret_cast<const float2*>(&S.w2f[0][8 * nt + 2 * ft]);   // W2[8][j], full fp32
+                    const float2 w9 = *reinterpret_cast<const float2*>(&S.w2f[1][8 * nt + 2 * ft]);   // W2[9][j]
 #pragma unroll
                     for (int mtl = 0; mtl < 2; ++mtl) {
                         float c[4] = {0.f, 0.f, 0.f, 0.f};
                         mma(c, el[mtl][0], m0h, m4h); mma(c, eh[mtl][0], m0l, m4l); mma(c, eh[mtl][0], m0h, m4h);
                         mma(c, el[mtl][1], m8h, 0u);  mma(c, eh[mtl][1], m8l, 0u);  mma(c, eh[mtl][1], m8h, 0u);
                         // c0:(g, 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)  ->  A of stage G: a0:(g, t) a1:(g+8, t) a2:(g, t+4) a3:(g+8, t+4)
+                        const float a00 = fmaxf(c[0] + b1v.x, 0.f), a10 = fmaxf(c[2] + b1v.x, 0.f);   // (g, 2t)  (g+8, 2t)
+                        const float a01 = fmaxf(c[1] + b1v.y, 0.f), a11 = fmaxf(c[3] + b1v.y, 0.f);   // (g, 2t+1) (g+8, 2t+1)
                         uint32_t ah[4], al[4];
-                        split(fmaxf(c[0] + b1v.x, 0.f), ah[0], al[0]);
-                        split(fmaxf(c[2] + b1v.x, 0.f), ah[1], al[1]);
-                        split(fmaxf(c[1] + b1v.y, 0.f), ah[2], al[2]);
-                        split(fmaxf(c[3] + b1v.y, 0.f), ah[3], al[3]);
-#pragma unroll
-                        for (int kt = 0; kt < 2; ++kt) {
-                            mma(gacc[mtl][kt], al, wh[kt].x, wh[kt].y);
-                            mma(gacc[mtl][kt], ah, wl[kt].x, wl[kt].y);
-                            mma(gacc[mtl][kt], ah, wh[kt].x, wh[kt].y);
-                        }
+                        split(a00, ah[0], al[0]);
+                        split(a10, ah[1], al[1]);
+                        split(a01, ah[2], al[2]);
+                        split(a11, ah[3], al[3]);
+                        mma(gacc[mtl], al, wh.x, wh.y);
+                        mma(gacc[mtl], ah, wl.x, wl.y);
+                        mma(gacc[mtl], ah, wh.x, wh.y);
+                        g89[mtl][0] = fmaf(w8.x, a00, fmaf(w8.y, a01, g89[mtl][0]));   // k = 8, row g
+                        g89[mtl][1] = fmaf(w9.x, a00, fmaf(w9.y, a01, g89[mtl][1]));   // k = 9, row g
+                        g89[mtl][2] = fmaf(w8.x, a10, fmaf(w8.y, a11, g89[mtl][2]));   // k = 8, row g+8
+                        g89[mtl][3] = fmaf(w9.x, a10, fmaf(w9.y, a11, g89[mtl][3]));   // k = 9, row g+8
                     }
                 }
 #pragma unroll
-                for (int mtl = 0; mtl < 2; ++mtl)
+                for (int mtl = 0; mtl < 2; ++mtl) {
+                    const int e = 16 * (2 * mp + mtl) + fg, k = 2 * ft;
+                    if (e < EMB)
+                        *reinterpret_cast<float2*>(urow + e * FC2 + k) = make_float2(fmaxf(gacc[mtl][0], 0.f), fmaxf(gacc[mtl][1], 0.f));
+                    if (e + 8 < EMB)
+                        *reinterpret_cast<float2*>(urow + (e + 8) * FC2 + k) = make_float2(fmaxf(gacc[mtl][2], 0.f), fmaxf(gacc[mtl][3], 0.f));
 #pragma unroll
-                    for (int kt = 0; kt < 2; ++kt) {
-                        const int e = 16 * (2 * mp + mtl) + fg, k = 8 * kt + 2 * ft;
-                        if (k < FC2) {
-                            if (e < EMB)
-                                *reinterpret_cast<float2*>(urow + e * FC2 + k) =
-                                    make_float2(fmaxf(gacc[mtl][kt][0], 0.f), fmaxf(gacc[mtl][kt][1], 0.f));
-                            if (e + 8 < EMB)
-                                *reinterpret_cast<float2*>(urow + (e + 8) * FC2 + k) =
-                                    make_float2(fmaxf(gacc[mtl][kt][2], 0.f), fmaxf(gacc[mtl][kt][3], 0.f));
-                        }
+                    for (int i = 0; i < 4; ++i) {                      // finish k = 8, 9 over the 4 lanes that share rows g, g+8
+                        g89[mtl][i] += __shfl_xor_sync(0xffffffffu, g89[mtl][i], 1);
+                        g89[mtl][i] += __shfl_xor_sync(0xffffffffu, g89[mtl][i], 2);
                     }
+                    if (ft == 0) {
+                        const float b8 = S.b2p[8], b9 = S.b2p[9];
+                        if (e < EMB)
+                            *reinterpret_cast<float2*>(urow + e * FC2 + 8) = make_float2(fmaxf(g89[mtl][0] + b8, 0.f), fmaxf(g89[mtl][1] + b9, 0.f));
+                        if (e + 8 < EMB)
+                            *reinterpret_cast<float2*>(urow + (e + 8) * FC2 + 8) = make_float2(fmaxf(g89[mtl][2] + b8, 0.f), fmaxf(g89[mtl][3] + b9, 0.f));
+                    }
+                }
             }
             if (lane < (IN0P - IN0) / 4)                               // zero the k-padding of the row
                 reinterpret_cast<float4*>(urow + IN0)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);

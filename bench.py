@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -75,16 +75,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if windows and not any(a <= ts <= b for a, b in windows):
+                continue                                                # keep only samples taken inside a timed region
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for nm, v in zip(names, r[4:8]):
@@ -260,15 +262,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
         e0.record(main)
         run_steps(K, labels_all)
         gathered = rdist.gather_labels(labels_all.view(K * batch, COLS), K * batch * world) if world > 1 else None
         e1.record(main)
         torch.cuda.synchronize()
+        tw1 = time.perf_counter()
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -302,6 +305,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = K * batch * world / e2e_s
+    # clocks sampled inside the two timed regions (device-resident steps, end-to-end call)
+    clocks = sampler.stop([(tw0, tw1), (t0, t0 + e2e_s)]) if rank == 0 else None
     del x_host
 
     # ---- per-kernel device times (CUDA events between the kernels of the chain) -> roofline --------
@@ -418,7 +423,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)

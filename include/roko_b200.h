@@ -102,6 +102,29 @@ int roko_b200_forward_timed(roko_b200_model* m, const uint8_t* x, int n_windows,
                             float* stage_ms);
 int roko_b200_measure_fp32_peak(int device, double* tflops);
 
+/* ---- training path (reference roko/train.py:41-55 calls model(x) in train mode and backpropagates
+ * F.cross_entropy through it) ---------------------------------------------
+ * train_forward: the train-mode forward of roko/rnn_model.py:46-59 -- the four dropout sites
+ *   (rnn_model.py:29,32,35 and nn.GRU's inter-layer dropout :41) active with probability `p_drop`
+ *   (0 turns them off: the eval-mode function, differentiable) and masks derived from `seed`.
+ *   x (n_windows,200,90) uint8, logits (n_windows,90,5) fp32, both device.  n_windows <= 1024.
+ *   `tws` (roko_b200_train_workspace_bytes(n_windows), about 8.1 MB per window, 16-byte aligned)
+ *   receives the saved activations; hand the same buffer, x, p_drop and seed to train_backward.
+ * train_backward: given dlogits = dLoss/dlogits (n_windows,90,5), writes the gradient of every
+ *   parameter into grad_raw: 1 099 731 fp32 in state_dict order, the layout roko_b200_model_load reads.
+ *   Consumes `tws` (one backward per forward).  The cross-entropy itself (train.py:52) stays with the caller.
+ * dropout_mask: the keep mask (1 = kept) these kernels use for `site` and element indices 0..n-1 in the
+ *   reference tensor's row-major order -- sites: 0 embedding (B,200,90,50), 1 fc1 (B,90,50,100),
+ *   2 fc2 (B,90,50,10), 3 / 4 output of GRU layer 0 / 1 (B,90,256).  For tests. */
+size_t roko_b200_train_workspace_bytes(int n_windows);
+int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows, float p_drop,
+                            unsigned long long seed, float* logits, void* tws, size_t tws_bytes, void* stream);
+int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows, float p_drop,
+                             unsigned long long seed, const float* dlogits, float* grad_raw, void* tws,
+                             size_t tws_bytes, void* stream);
+int roko_b200_dropout_mask(float p_drop, unsigned long long seed, int site, size_t n, uint8_t* mask_out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

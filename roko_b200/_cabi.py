@@ -39,6 +39,15 @@ SIGNATURES = {
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int,
                                                ctypes.POINTER(ctypes.c_float)]),
     "roko_b200_measure_fp32_peak": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "roko_b200_train_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "roko_b200_train_forward": (ctypes.c_int, [c_model_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                               ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_size_t, ctypes.c_void_p]),
+    "roko_b200_train_backward": (ctypes.c_int, [c_model_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                                ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "roko_b200_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_size_t,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -7,13 +7,13 @@
 #include <new>
 
 #include "../../include/roko_b200.h"
-#include "common.cuh"
+#include "model.h"
 
 using namespace roko;
 
 namespace {
 
-thread_local char g_err[512] = "";
+thread_local char g_err[ROKO_ERRBUF] = "";
 
 int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -28,7 +28,6 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
 
 constexpr size_t WIN_BYTES = (size_t)READS * COLS;                  // 18 000
 constexpr size_t WS_WIN_BYTES = WS_PER_WINDOW * sizeof(float) + WIN_BYTES;
-constexpr int NSLOT = 3;
 
 struct DeviceGuard {
     int prev = -1;
@@ -42,28 +41,6 @@ struct DeviceGuard {
 
 }  // namespace
 
-struct roko_b200_model {
-    int device = 0;
-    int num_sms = 148;
-    float* packed = nullptr;
-    float* raw_stage = nullptr;
-    int* status = nullptr;          // device flag word, bit 0: code outside 0..11
-    bool loaded = false;
-    int use_tc = 3;                 // projection: 3 = persistent tcgen05, double-buffered accumulators (proj_tc3.cu, default);
-                                    // ROKO_B200_PROJ=tc2 -> 256x256 tile, tc1 -> 128x256 tile, ffma -> FFMA SGEMM
-    int superbatch = 2368;          // windows per device pass of infer_host (148 SMs x 16; ROKO_B200_SUPERBATCH)
-    int rec_tc_min = 256;           // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never)
-    FrontConst fc;
-    struct Slot {
-        cudaStream_t stream = nullptr;
-        cudaEvent_t done = nullptr;
-        uint8_t* x = nullptr;
-        uint8_t* labels = nullptr;
-        float* logits = nullptr;
-        void* ws = nullptr;
-    } slot[NSLOT];
-    int slot_cap = 0;
-};
 
 namespace {
 
@@ -96,14 +73,7 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
         float* outs[3] = {h0, h1, h0};
         for (int l = 0; l < LAYERS; ++l) {
             if (ev) CU(cudaEventRecord(ev[1 + 2 * l], s));
-            if (m->use_tc == 3)
-                CU(launch_proj_tc3(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, m->num_sms, s));
-            else if (m->use_tc == 2)
-                CU(launch_proj_tc2(in, gru_inp(l), pk + pk_wt2(l), pk + pk_bgi(l), gi, rows, s));
-            else if (m->use_tc)
-                CU(launch_proj_tc(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, s));
-            else
-                CU(launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s));
+            CU(proj_dispatch(m, in, l, gi, rows, s));
             if (ev) CU(cudaEventRecord(ev[2 + 2 * l], s));
             // (>= 64 windows also keeps rec_tc's unguarded gi reads of a ragged last group inside the scratch)
             if (m->rec_tc_min > 0 && nc >= m->rec_tc_min && nc >= 64)
@@ -150,6 +120,8 @@ int ensure_slots(roko_b200_model* m, int batch) {
 }
 
 }  // namespace
+
+char* roko_b200_errbuf() { return g_err; }
 
 extern "C" {
 
@@ -210,12 +182,9 @@ int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device
     if (!m || !raw) return fail(ROKO_B200_EARG, "model / raw is NULL%s%s");
     DeviceGuard g(m->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const float* src = raw;
-    if (!raw_on_device) {
-        CU(cudaMemcpyAsync(m->raw_stage, raw, (size_t)RAW_TOTAL * sizeof(float), cudaMemcpyHostToDevice, s));
-        src = m->raw_stage;
-    }
-    CU(launch_pack(src, m->packed, s));
+    CU(cudaMemcpyAsync(m->raw_stage, raw, (size_t)RAW_TOTAL * sizeof(float),
+                       raw_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CU(launch_pack(m->raw_stage, m->packed, s));
     // W2 / b1 / b2 ride in the front-end kernel's parameter bank: keep a host copy
     if (raw_on_device) {
         CU(cudaMemcpyAsync(m->fc.W2, raw + RAW_W2, sizeof(m->fc.W2), cudaMemcpyDeviceToHost, s));

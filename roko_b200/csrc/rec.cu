@@ -14,7 +14,7 @@
 // the layer output.  gi for step s+1 is prefetched while step s computes.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "train.cuh"
 
 namespace roko {
 
@@ -42,10 +42,11 @@ __device__ __forceinline__ float tanh_f(float v) {
 }
 #endif
 
-template <int NB>
+// SAVE (training forward): also file (r, z, n, W_hn h + b_hn) per (row, direction, unit) for the backward.
+template <int NB, bool SAVE>
 __global__ void __launch_bounds__(REC_THREADS, 1)
 rec_kernel(const float* __restrict__ gi, const float* __restrict__ whh0, size_t dir_stride,
-           const float* __restrict__ bhn0, float* __restrict__ out, int nwin) {
+           const float* __restrict__ bhn0, float* __restrict__ out, int nwin, float4* __restrict__ gates) {
     static_assert(NB == 1 || NB == 2 || NB == 4, "group size");
     __shared__ __align__(16) float hs[2][NB][HS_STRIDE];
     const int tid = threadIdx.x, j = tid >> 2, kq = tid & 3;
@@ -67,6 +68,7 @@ rec_kernel(const float* __restrict__ gi, const float* __restrict__ whh0, size_t 
         // 32-bit element offsets (a chunk is far below 2^31 floats): fewer live registers
         unsigned gofs = (unsigned)(row0 + t) * GI_N + dir * G3 + j * 3;
         unsigned oofs = (unsigned)(row0 + t) * OUT_W + dir * HID + j;
+        unsigned sofs = ((unsigned)(row0 + t) * 2 + dir) * HID + j;
         const int gstep = dt * GI_N, ostep = dt * OUT_W;
 
         __syncthreads();                                     // previous group's readers are done
@@ -135,6 +137,7 @@ rec_kernel(const float* __restrict__ gi, const float* __restrict__ whh0, size_t 
                 hprev = h;
                 hs[cur ^ 1][kq][j] = h;
                 out[oofs] = h;
+                if (SAVE) { gates[sofs] = make_float4(r, z, n, a_n + bhn); sofs += dt * 2 * HID; }
                 gofs += gstep; oofs += ostep;
                 if (s + 1 < COLS) { g_r = gi[gofs]; g_z = gi[gofs + 1]; g_n = gi[gofs + 2]; }   // a full step ahead
             }
@@ -169,9 +172,36 @@ cudaError_t launch_rec(const float* gi, const float* whh_d0, size_t dir_stride, 
     if (g_force_nb == 1 || g_force_nb == 2 || g_force_nb == 4) nb = g_force_nb;
     const int ngroups = (nwin + nb - 1) / nb;
     const int grid = 2 * (ngroups < pairs ? ngroups : pairs);
-    if (nb == 1) rec_kernel<1><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin);
-    else if (nb == 2) rec_kernel<2><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin);
-    else rec_kernel<4><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin);
+    if (nb == 1) rec_kernel<1, false><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, nullptr);
+    else if (nb == 2) rec_kernel<2, false><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, nullptr);
+    else rec_kernel<4, false><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, nullptr);
+    return cudaGetLastError();
+}
+
+int rec_pick_nb(int nwin, int num_sms) {
+    if (g_force_nb == 1 || g_force_nb == 2 || g_force_nb == 4) return g_force_nb;
+    const int pairs = num_sms / 2;
+    int nb = 1;
+    double best = 1e30;
+    for (int cand = 1; cand <= 4; cand *= 2) {
+        const int groups = (nwin + cand - 1) / cand;
+        const int rounds = (groups + pairs - 1) / pairs;
+        const double cost = rounds * (REC_C0 + REC_C1 * cand);
+        if (cost < best) { best = cost; nb = cand; }
+    }
+    return nb;
+}
+
+cudaError_t launch_rec_train(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
+                             float* out, float4* gates, int nwin, int num_sms, cudaStream_t s) {
+    if (nwin <= 0) return cudaSuccess;
+    const int pairs = num_sms / 2;
+    const int nb = rec_pick_nb(nwin, num_sms);
+    const int ngroups = (nwin + nb - 1) / nb;
+    const int grid = 2 * (ngroups < pairs ? ngroups : pairs);
+    if (nb == 1) rec_kernel<1, true><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, gates);
+    else if (nb == 2) rec_kernel<2, true><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, gates);
+    else rec_kernel<4, true><<<grid, REC_THREADS, 0, s>>>(gi, whh_d0, dir_stride, bhn_d0, out, nwin, gates);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,71 @@
+// Declarations shared by the training-path translation units (gemm.cu, train.cu, rec_bwd.cu,
+// train_api.cu).  The training forward is the reference's train-mode forward
+// (roko/rnn_model.py:46-59 with the four dropout sites :29,:32,:35,:41 active) and its backward is
+// what autograd derives for roko/train.py:46-53.
+#pragma once
+#include "common.cuh"
+
+namespace roko {
+
+// ---- dropout: counter-based masks, reproducible from (seed, site, element index) ---------------
+// Site element indices follow the reference tensors' own row-major order:
+//   DROP_EMB  (B,200,90,50)   DROP_FC1 (B,90,50,100)   DROP_FC2 (B,90,50,10)   DROP_GRU0/1 (B,90,256)
+enum { DROP_EMB = 0, DROP_FC1 = 1, DROP_FC2 = 2, DROP_GRU0 = 3, DROP_GRU1 = 4, DROP_SITES = 5 };
+
+struct DropCfg {
+    unsigned long long seed;
+    unsigned int thresh;     // drop when hash < thresh;  thresh = round(p * 2^32), 0 = keep everything
+    float scale;             // 1 / (1 - p)
+};
+
+__host__ __device__ __forceinline__ unsigned int drop_hash(unsigned long long seed, unsigned int site,
+                                                           unsigned long long idx) {
+    // splitmix64 finaliser over (seed, site, idx)
+    unsigned long long z = idx + (seed ^ ((unsigned long long)(site + 1) * 0xD1B54A32D192ED03ull));
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (unsigned int)(z >> 32);
+}
+__host__ __device__ __forceinline__ bool drop_keep(const DropCfg& d, unsigned int site, unsigned long long idx) {
+    return d.thresh == 0u || drop_hash(d.seed, site, idx) >= d.thresh;
+}
+
+// ---- general GEMM (gemm.cu) --------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_ACC = 1, EPI_ATOMIC = 2, EPI_FC1 = 3 };
+struct GemmArgs {
+    const float* A; const float* B; float* C;
+    int M, N, K, lda, ldb, ldc;
+    const float* bias;       // EPI_FC1
+    DropCfg drop;            // EPI_FC1
+    int kchunk;              // filled by the launcher
+    bool vecA, vecB;         // filled by the launcher
+};
+cudaError_t launch_gemm(GemmArgs g, bool ka, bool kb, int epi, int splits, int num_sms, cudaStream_t s);
+
+// ---- element-wise / small kernels (train.cu) -----------------------------------------------------
+cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, int nwin, DropCfg d, int* status,
+                              cudaStream_t s);
+cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, float* u, int rows50, DropCfg d,
+                           cudaStream_t s);
+cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2,
+                           int rows50, float scale, int num_sms, cudaStream_t s);
+cudaError_t launch_drop_apply(const float* in, float* out, size_t n, unsigned int site, DropCfg d, cudaStream_t s);
+cudaError_t launch_colsum(const float* A, int lda, int rows, int ncols, float* out, cudaStream_t s);
+cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, float* dE, int nwin, DropCfg d, int num_sms,
+                              cudaStream_t s);
+cudaError_t launch_drop_mask(unsigned int site, size_t n, uint8_t* out, DropCfg d, cudaStream_t s);
+
+// ---- recurrence (rec.cu forward with gate saving, rec_bwd.cu) -------------------------------------
+// gates: [row][dir][j] float4 (r, z, n, W_hn h + b_hn)
+cudaError_t launch_rec_train(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,
+                             float* out, float4* gates, int nwin, int num_sms, cudaStream_t s);
+// dgi [row][768] (n = d*384 + g*128 + j), dghn [row][256], dgh_prev [row][768] (the recurrent-side
+// gate gradients filed under the row whose output was that step's h_prev; zero where there is none)
+cudaError_t launch_rec_bwd(const float* dout, const float4* gates, const float* out, const float* whh_raw_d0,
+                           size_t raw_dir_stride, float* dgi, float* dghn, float* dgh_prev, int nwin, int num_sms,
+                           cudaStream_t s);
+cudaError_t rec_bwd_setup();
+
+}  // namespace roko

@@ -9,8 +9,12 @@ Reference interface mirrored here (file:line in /root/reference):
   * ``RNN.forward(x) -> (B, 90, 5)`` fp32 logits                        roko/rnn_model.py:46-59
   * callers do ``from rnn_model import *`` and use ``nn`` / ``F``       roko/inference.py:9, train.py:10
 
+``forward`` is differentiable: in train mode (dropout active) or whenever autograd needs parameter
+gradients it runs the training kernels with a hand-written backward (roko/train.py:46-53).
+
 Additions (not in the reference): ``predict`` (fused argmax, uint8 labels), ``predict_host``
-(pipelined host-buffer loop), ``forward_taps`` (stage outputs for parity tests).
+(pipelined host-buffer loop), ``forward_taps`` (stage outputs for parity tests),
+``dropout_masks`` (the training kernels' keep-masks, for tests).
 
 There is no CPU path: a CPU tensor, a missing library or a non-sm_100 device raise.
 """
@@ -31,6 +35,7 @@ NUM_LAYERS = 3
 
 READS, COLS, CLASSES = 200, 90, 5
 MAX_CHUNK = 2368          # windows per internal chunk = 148 SMs x 16 (bounds scratch: 0.66 MB / window)
+MAX_TRAIN_BATCH = 1024    # windows per training forward/backward (8.1 MB of saved activations each)
 
 
 def gru_init(gru):
@@ -68,6 +73,71 @@ class _Handle:
                 self.ptr = None
         except Exception:
             pass
+
+
+DROPOUT_SITES = {"emb": (READS, COLS, 50), "fc1": (COLS, 50, 100), "fc2": (COLS, 50, 10),
+                 "gru0": (COLS, 2 * HIDDEN_SIZE), "gru1": (COLS, 2 * HIDDEN_SIZE)}
+
+
+def dropout_masks(p_drop, seed, batch, device):
+    """Keep-masks (uint8, 1 = kept) the training kernels derive from ``seed`` for a batch, one per
+    dropout site, shaped like the reference tensor each site masks (roko/rnn_model.py:47,51,54,57)."""
+    lib = _cabi.lib()
+    dev = torch.device(device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    out = {}
+    with torch.cuda.device(dev):
+        for site, (name, shape) in enumerate(DROPOUT_SITES.items()):
+            m = torch.empty((batch,) + shape, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.roko_b200_dropout_mask(float(p_drop), int(seed), site, m.numel(), m.data_ptr(), stream))
+            out[name] = m
+    return out
+
+
+class _TrainFn(torch.autograd.Function):
+    """Train-mode forward / backward of the whole network as two C-ABI calls.
+
+    The parameters are inputs of the Function, so autograd routes the gradients the library
+    writes (one flat fp32 buffer in state_dict order) to ``param.grad`` like any other op --
+    optimisers, ``zero_grad`` and DDP's gradient hooks work unchanged.
+    """
+
+    @staticmethod
+    def forward(ctx, module, x8, p_drop, seed, *params):
+        h = module._handle(x8.device)
+        n, idx = x8.shape[0], h.device_index
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        tws = torch.empty(h.lib.roko_b200_train_workspace_bytes(n), dtype=torch.uint8, device=x8.device)
+        logits = torch.empty((n, COLS, CLASSES), dtype=torch.float32, device=x8.device)
+        _cabi.check(h.lib.roko_b200_train_forward(h.ptr, x8.data_ptr(), n, p_drop, seed, logits.data_ptr(),
+                                                  tws.data_ptr(), tws.numel(), stream))
+        ctx.h, ctx.x8, ctx.p_drop, ctx.seed, ctx.tws, ctx.version = h, x8, p_drop, seed, tws, h.version
+        ctx.shapes = [tuple(q.shape) for q in params]
+        return logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dlogits):
+        h = ctx.h
+        if ctx.tws is None:
+            raise RuntimeError("roko_b200: backward through the same forward twice (the saved activations "
+                               "are consumed by the first backward)")
+        if h.version != ctx.version:
+            raise RuntimeError("roko_b200: parameters changed between forward and backward")
+        n, idx = ctx.x8.shape[0], h.device_index
+        dlogits = dlogits.to(torch.float32).contiguous()
+        stream = torch.cuda.current_stream(idx).cuda_stream
+        grad_raw = torch.empty(h.lib.roko_b200_raw_weight_count(), dtype=torch.float32, device=dlogits.device)
+        _cabi.check(h.lib.roko_b200_train_backward(h.ptr, ctx.x8.data_ptr(), n, ctx.p_drop, ctx.seed,
+                                                   dlogits.data_ptr(), grad_raw.data_ptr(), ctx.tws.data_ptr(),
+                                                   ctx.tws.numel(), stream))
+        ctx.tws = None
+        grads, off = [], 0
+        for shape in ctx.shapes:
+            k = math.prod(shape)
+            grads.append(grad_raw[off:off + k].view(shape))
+            off += k
+        return (None, None, None, None, *grads)
 
 
 class RNN(nn.Module):
@@ -164,12 +234,36 @@ class RNN(nn.Module):
 
     # ---- reference interface ------------------------------------------------------------------
     def forward(self, x):
-        """``(B,200,90)`` uint8|int64 codes 0..11 on a CUDA device -> ``(B,90,5)`` fp32 logits."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "roko_b200.RNN implements the inference path (eval mode / no_grad); the training "
-                "forward with dropout and autograd (roko/train.py:46-53) is not built yet")
-        return self._run(x, True, False)[0]
+        """``(B,200,90)`` uint8|int64 codes 0..11 on a CUDA device -> ``(B,90,5)`` fp32 logits.
+
+        Inference (eval mode, nothing to differentiate) runs the fused inference kernels.  In train mode,
+        or whenever autograd is recording and a parameter requires grad, it runs the training kernels:
+        the same network with the four dropout sites of roko/rnn_model.py:29,32,35,41 active (train mode)
+        and a hand-written backward behind ``torch.autograd`` (roko/train.py:46-53).
+        """
+        differentiate = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not self.training and not differentiate:
+            return self._run(x, True, False)[0]
+        return self._train_forward(x)
+
+    def _dropout_p(self):
+        ps = {float(self.do.p), float(self.do1.p), float(self.do2.p), float(self.gru.dropout)}
+        if len(ps) != 1:
+            raise RuntimeError("roko_b200 kernels use one dropout probability for all four sites "
+                               f"(roko/rnn_model.py:25 passes a single `dropout`); got {sorted(ps)}")
+        return ps.pop() if self.training else 0.0
+
+    def _train_forward(self, x, seed=None):
+        x = self._check_input(x)
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        if x.shape[0] == 0:
+            return torch.zeros((0, COLS, CLASSES), dtype=torch.float32, device=x.device)
+        if x.shape[0] > MAX_TRAIN_BATCH:
+            raise RuntimeError(f"training batches hold at most {MAX_TRAIN_BATCH} windows (got {x.shape[0]})")
+        if seed is None:                      # drawn from torch's CPU generator: torch.manual_seed reproduces a run
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return _TrainFn.apply(self, x, self._dropout_p(), int(seed), *self._ordered_params())
 
     # ---- additions ----------------------------------------------------------------------------
     @torch.no_grad()

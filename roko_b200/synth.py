@@ -20,7 +20,7 @@ def uniform_windows(n, seed=1234):
     return rng.integers(0, N_CODES, size=(n, READS, COLS), dtype=np.uint8)
 
 
-def structured_windows(n, seed=101):
+def structured_windows(n, seed=101, return_truth=False):
     rng = np.random.Generator(np.random.PCG64(seed))
     truth = rng.integers(0, 5, size=(n, 1, COLS), dtype=np.uint8)
     x = np.broadcast_to(truth, (n, READS, COLS)).copy()
@@ -32,4 +32,5 @@ def structured_windows(n, seed=101):
     x[prefix] = 5
     strand = rng.random((n, READS, 1)) < 0.5
     x = x + (6 * strand).astype(np.uint8)
-    return np.ascontiguousarray(x, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    return (x, truth[:, 0, :].copy()) if return_truth else x

@@ -44,9 +44,27 @@ def edge():
 
 @pytest.fixture(scope="session")
 def cuda_model(seed1_state):
-    """The product path: roko_b200.RNN on cuda:0 with the golden weights (fails loudly w/o GPU/.so)."""
+    """The product path: roko_b200.RNN on cuda:0 with the golden weights (fails loudly w/o GPU/.so).
+
+    Inference fixture: parameters frozen, so ``model(x)`` takes the inference kernels whether or not
+    the caller wrapped it in ``torch.no_grad()`` (the trainable twin is ``train_model``)."""
     import torch
     from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
     m = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
     m.load_state_dict(seed1_state, strict=True)
-    return m.to("cuda:0").eval()
+    return m.to("cuda:0").eval().requires_grad_(False)
+
+
+@pytest.fixture()
+def train_model(seed1_state):
+    """A fresh trainable roko_b200.RNN on cuda:0 with the golden weights."""
+    from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+    m = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
+    m.load_state_dict(seed1_state, strict=True)
+    return m.to("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def train_golden():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "train_seed1.npz")))

@@ -4,14 +4,16 @@
 //   KA = true : A(m,k) = A[m*lda + k]   (k contiguous)      KA = false: A(m,k) = A[k*lda + m]
 //   KB = true : B(k,n) = B[n*ldb + k]   (k contiguous)      KB = false: B(k,n) = B[k*ldb + n]
 //
-// FP32 FFMA, 128x128x8 tiles, 256 threads, 8x8 register micro-tile, register-prefetch double
-// buffering (same engine as proj.cu).  gridDim.z splits K; split launches add with atomics into a
-// zeroed C.  Epilogues: store, accumulate, atomic add, and fc1's bias + ReLU + dropout.
+// 3xTF32 on mma.sync.m16n8k8 (fp32-level accuracy, see split_tf32), 128x128x8 tiles, 256 threads,
+// register-prefetch double buffering through k-major shared tiles.  gridDim.z splits K; split
+// launches add with atomics into a zeroed C.  Epilogues: store, accumulate, atomic add, and fc1's
+// bias + ReLU + dropout.
 #include "train.cuh"
 
 namespace roko {
 
-constexpr int GM = 128, GN = 128, GK = 8, G_THREADS = 256, GTS = 132;
+constexpr int GM = 128, GN = 128, GK = 8, G_THREADS = 256;
+constexpr int GTS = 136;     // row stride = 8 (mod 32) floats: the mma fragment reads (k = lane&3, row = lane>>2) hit 32 banks
 
 template <bool KCONTIG>
 __device__ __forceinline__ void tile_load(const float* __restrict__ P, int ld, int row0, int nrows, int k0,
@@ -57,11 +59,26 @@ __device__ __forceinline__ void tile_store(float (*T)[GTS], int tid, const float
     }
 }
 
+// tf32 split: x = hi + lo with hi = rna(x) on 10 mantissa bits; the tensor core reads the top 19 bits of lo
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// 8 warps as 4 (m) x 2 (n): a warp owns 32 x 64 of the 128 x 128 tile = 2 x 8 m16n8k8 accumulators.
+// Every product is 3xTF32 (lo*hi + hi*lo + hi*hi, small terms first): fp32-level accuracy on the tensor pipe.
 template <bool KA, bool KB, int EPI>
 __global__ void __launch_bounds__(G_THREADS, 2) sgemm_kernel(const GemmArgs g) {
     __shared__ __align__(16) float As[2][GK][GTS];
     __shared__ __align__(16) float Bs[2][GK][GTS];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     const int kbeg = blockIdx.z * g.kchunk;
     const int kend = (kbeg + g.kchunk) < g.K ? (kbeg + g.kchunk) : g.K;
@@ -73,11 +90,13 @@ __global__ void __launch_bounds__(G_THREADS, 2) sgemm_kernel(const GemmArgs g) {
     tile_store<KB>(Bs[0], tid, rb);
     __syncthreads();
 
-    float acc[8][8];
+    float acc[2][8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
 
     const int KT = (kend - kbeg + GK - 1) / GK;
     for (int kt = 0; kt < KT; ++kt) {
@@ -86,18 +105,27 @@ __global__ void __launch_bounds__(G_THREADS, 2) sgemm_kernel(const GemmArgs g) {
             tile_load<KA>(g.A, g.lda, m0, g.M, kbeg + (kt + 1) * GK, kend, g.vecA, tid, ra);
             tile_load<KB>(g.B, g.ldb, n0, g.N, kbeg + (kt + 1) * GK, kend, g.vecB, tid, rb);
         }
+        uint32_t ah[2][4], al[2][4];
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int i = 0; i < 2; ++i) {
+            const int m = wm + i * 16 + gq;
+            split_tf32(As[buf][tq][m], ah[i][0], al[i][0]);
+            split_tf32(As[buf][tq][m + 8], ah[i][1], al[i][1]);
+            split_tf32(As[buf][tq + 4][m], ah[i][2], al[i][2]);
+            split_tf32(As[buf][tq + 4][m + 8], ah[i][3], al[i][3]);
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+            const int n = wn + j * 8 + gq;
+            uint32_t bh[2], bl[2];
+            split_tf32(Bs[buf][tq][n], bh[0], bl[0]);
+            split_tf32(Bs[buf][tq + 4][n], bh[1], bl[1]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < 2; ++i) {
+                mma_tf32(acc[i][j], al[i], bh);
+                mma_tf32(acc[i][j], ah[i], bl);
+                mma_tf32(acc[i][j], ah[i], bh);
+            }
         }
         if (kt + 1 < KT) {
             tile_store<KA>(As[buf ^ 1], tid, ra);
@@ -107,25 +135,31 @@ __global__ void __launch_bounds__(G_THREADS, 2) sgemm_kernel(const GemmArgs g) {
     }
 
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-        if (m >= g.M) continue;
+    for (int i = 0; i < 2; ++i) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-            if (n >= g.N) continue;
-            float* c = g.C + (size_t)m * g.ldc + n;
-            float v = acc[i][j];
-            if (EPI == EPI_STORE) {
-                *c = v;
-            } else if (EPI == EPI_ACC) {
-                *c += v;
-            } else if (EPI == EPI_ATOMIC) {
-                atomicAdd(c, v);
-            } else {   // EPI_FC1: relu(v + b1[n]) then dropout site 1, element index m*N + n
-                v = fmaxf(v + __ldg(g.bias + n), 0.f);
-                v = drop_keep(g.drop, DROP_FC1, (unsigned long long)m * g.N + n) ? v * g.drop.scale : 0.f;
-                *c = v;
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + wm + i * 16 + gq + h * 8;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int n = n0 + wn + j * 8 + tq * 2 + c;
+                    if (n >= g.N) continue;
+                    float* cp = g.C + (size_t)m * g.ldc + n;
+                    float v = acc[i][j][h * 2 + c];
+                    if (EPI == EPI_STORE) {
+                        *cp = v;
+                    } else if (EPI == EPI_ACC) {
+                        *cp += v;
+                    } else if (EPI == EPI_ATOMIC) {
+                        atomicAdd(cp, v);
+                    } else {   // EPI_FC1: relu(v + b1[n]) then dropout site 1, element index m*N + n
+                        v = fmaxf(v + __ldg(g.bias + n), 0.f);
+                        v = drop_keep(g.drop, DROP_FC1, (unsigned long long)m * g.N + n) ? v * g.drop.scale : 0.f;
+                        *cp = v;
+                    }
+                }
             }
         }
     }

@@ -12,9 +12,10 @@ constexpr int TR_THREADS = 256;
 constexpr int PE = EMB * READS;           // 10 000 embedding outputs per (window, column)
 
 // ep[(b,p,e)][r] = dropout(E[x[b][r][p]][e])                       rnn_model.py:47-48 (+ permute)
+// The keep bits of the block's 10 000 outputs are filed as 313 words (MASK_WORDS per block) for the backward.
 __global__ void __launch_bounds__(TR_THREADS)
 embed_drop_kernel(const uint8_t* __restrict__ x, const float* __restrict__ E, float* __restrict__ ep,
-                  DropCfg d, int* __restrict__ status) {
+                  uint32_t* __restrict__ bits, DropCfg d, int* __restrict__ status) {
     __shared__ float Es[NCODES * EMB];
     __shared__ uint8_t codes[READS];
     const int bp = blockIdx.x, b = bp / COLS, p = bp - b * COLS, tid = threadIdx.x;
@@ -26,11 +27,18 @@ embed_drop_kernel(const uint8_t* __restrict__ x, const float* __restrict__ E, fl
     }
     __syncthreads();
     float* dst = ep + (size_t)bp * PE;
-    for (int idx = tid; idx < PE; idx += TR_THREADS) {
-        const int e = idx / READS, r = idx - e * READS;
-        const float v = Es[codes[r] * EMB + e];
-        const unsigned long long i0 = (((unsigned long long)b * READS + r) * COLS + p) * EMB + e;
-        dst[idx] = drop_keep(d, DROP_EMB, i0) ? v * d.scale : 0.f;
+    uint32_t* bdst = bits + (size_t)bp * MASK_WORDS;
+    for (int idx = tid; idx < MASK_WORDS * 32; idx += TR_THREADS) {      // whole warps: the ballot needs all 32 lanes
+        bool keep = false;
+        if (idx < PE) {
+            const int e = idx / READS, r = idx - e * READS;
+            const float v = Es[codes[r] * EMB + e];
+            const unsigned long long i0 = (((unsigned long long)b * READS + r) * COLS + p) * EMB + e;
+            keep = drop_keep(d, DROP_EMB, i0);
+            dst[idx] = keep ? v * d.scale : 0.f;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, keep);
+        if ((tid & 31) == 0) bdst[idx >> 5] = word;
     }
 }
 
@@ -67,24 +75,20 @@ fc2_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ W2, const
 //   dg[k]  = du[(m,e),k] * scale * [u > 0]                 (u > 0  <=>  kept and pre-activation > 0)
 //   dW2   += dg (x) a1,  db2 += dg
 //   dap[j] = (sum_k dg[k] W2[k][j]) * scale * [a1[j] > 0]   written over a1
+// Thread (j, half) keeps column j of W2 and of the dW2 partial sums in registers and walks 32 rows
+// of the 64-row tile: per row one a1 value, the row's 10 dg (broadcast), 20 FMA.
 __global__ void __launch_bounds__(TR_THREADS)
 fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float* __restrict__ a1,
                const float* __restrict__ W2, float* __restrict__ dW2, float* __restrict__ db2, int rows50,
                float scale) {
     __shared__ float as[F2_ROWS][FC1];
-    __shared__ float ws[FC2][FC1];
-    __shared__ float dgs[F2_ROWS][FC2];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < FC2 * FC1; i += TR_THREADS) (&ws[0][0])[i] = W2[i];
-    float accw[4] = {0.f, 0.f, 0.f, 0.f};
-    float accb = 0.f;
-    int ok[4], oj[4];
+    __shared__ __align__(16) float dgs[F2_ROWS][12];        // 10 used, padded for LDS.128
+    const int tid = threadIdx.x, j = tid & 127, half = tid >> 7;
+    const bool active = j < FC1;
+    float w2c[FC2], accw[FC2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int o = tid + i * TR_THREADS;
-        ok[i] = o < FC2 * FC1 ? o / FC1 : -1;
-        oj[i] = o % FC1;
-    }
+    for (int k = 0; k < FC2; ++k) { w2c[k] = active ? W2[k * FC1 + j] : 0.f; accw[k] = 0.f; }
+    float accb = 0.f;
     const int ntiles = (rows50 + F2_ROWS - 1) / F2_ROWS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * F2_ROWS;
@@ -92,10 +96,10 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
         __syncthreads();                                    // previous tile's readers are done
         for (int i = tid; i < F2_ROWS * FC1; i += TR_THREADS)
             (&as[0][0])[i] = i < nrow * FC1 ? a1[(size_t)row0 * FC1 + i] : 0.f;
-        for (int i = tid; i < F2_ROWS * FC2; i += TR_THREADS) {
-            const int row = i / FC2, k = i - row * FC2;
+        for (int i = tid; i < F2_ROWS * 12; i += TR_THREADS) {
+            const int row = i / 12, k = i - row * 12;
             float v = 0.f;
-            if (row < nrow) {
+            if (row < nrow && k < FC2) {
                 const int g = row0 + row, m = g / EMB, e = g - m * EMB;
                 const size_t off = (size_t)m * IN0P + e * FC2 + k;
                 v = u[off] > 0.f ? du[off] * scale : 0.f;
@@ -103,26 +107,31 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
             dgs[row][k] = v;
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (ok[i] < 0) continue;
-            float a = accw[i];
-            for (int row = 0; row < F2_ROWS; ++row) a = fmaf(dgs[row][ok[i]], as[row][oj[i]], a);
-            accw[i] = a;
-        }
         if (tid < FC2)
             for (int row = 0; row < F2_ROWS; ++row) accb += dgs[row][tid];
-        for (int i = tid; i < nrow * FC1; i += TR_THREADS) {
-            const int row = i / FC1, j = i - row * FC1;
-            float da = 0.f;
+        if (active) {
+            const int rbeg = half * (F2_ROWS / 2);
+#pragma unroll 4
+            for (int row = rbeg; row < rbeg + F2_ROWS / 2; ++row) {
+                const float a = as[row][j];
+                const float4 d0 = *reinterpret_cast<const float4*>(&dgs[row][0]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&dgs[row][4]);
+                const float4 d2 = *reinterpret_cast<const float4*>(&dgs[row][8]);
+                const float dg[FC2] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y};
+                float da = 0.f;
 #pragma unroll
-            for (int k = 0; k < FC2; ++k) da = fmaf(dgs[row][k], ws[k][j], da);
-            a1[(size_t)row0 * FC1 + i] = as[row][j] > 0.f ? da * scale : 0.f;
+                for (int k = 0; k < FC2; ++k) {
+                    accw[k] = fmaf(dg[k], a, accw[k]);
+                    da = fmaf(dg[k], w2c[k], da);
+                }
+                if (row < nrow) a1[(size_t)(row0 + row) * FC1 + j] = a > 0.f ? da * scale : 0.f;
+            }
         }
     }
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (ok[i] >= 0) atomicAdd(dW2 + tid + i * TR_THREADS, accw[i]);
+        for (int k = 0; k < FC2; ++k) atomicAdd(dW2 + k * FC1 + j, accw[k]);
+    }
     if (tid < FC2) atomicAdd(db2 + tid, accb);
 }
 
@@ -159,49 +168,109 @@ colsum_kernel(const float* __restrict__ A, int lda, int rows, int ncols, float* 
 }
 
 // dE[c][e] += sum over (b, r, p) with x[b][r][p] == c of mask * scale * dep[(b,p,e)][r]    (embedding backward)
+// Per (window, column): the 50 x 200 tile of dep is staged with the forward's keep bits applied, the 200
+// reads are counting-sorted by code (stable, ballot based), and worker (c, e) adds tile[e][r] over the
+// reads of code c -- 10 000 adds per tile.  Partial sums stay in registers across tiles.
 __global__ void __launch_bounds__(TR_THREADS)
-embed_grad_kernel(const float* __restrict__ dep, const uint8_t* __restrict__ x, float* __restrict__ dE, int nwin,
-                  DropCfg d) {
+embed_grad_kernel(const float* __restrict__ dep, const uint8_t* __restrict__ x, const uint32_t* __restrict__ bits,
+                  float* __restrict__ dE, int nwin, float scale) {
     __shared__ float tile[EMB][READS + 1];
     __shared__ uint8_t codes[READS];
-    __shared__ float tab[NCODES * EMB];
-    const int tid = threadIdx.x;
-    const int e = tid / 5, rl = tid - e * 5;               // 250 workers: channel e, reads rl, rl+5, ...
-    float acc[NCODES];
-#pragma unroll
-    for (int c = 0; c < NCODES; ++c) acc[c] = 0.f;
-    for (int i = tid; i < NCODES * EMB; i += TR_THREADS) tab[i] = 0.f;
+    __shared__ uint8_t order[READS];                       // reads sorted by code
+    __shared__ int cbeg[NCODES + 1];
+    __shared__ int ccount[NCODES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float acc[3] = {0.f, 0.f, 0.f};                        // workers q = tid + 256 i < 600:  c = q / 50, e = q % 50
     const int nbp = nwin * COLS;
     for (int bp = blockIdx.x; bp < nbp; bp += gridDim.x) {
         const int b = bp / COLS, p = bp - b * COLS;
         __syncthreads();
         const float* src = dep + (size_t)bp * PE;
+        const uint32_t* bsrc = bits + (size_t)bp * MASK_WORDS;
         for (int i = tid; i < PE; i += TR_THREADS) {
             const int ee = i / READS;
-            tile[ee][i - ee * READS] = src[i];
+            const bool keep = (bsrc[i >> 5] >> (i & 31)) & 1u;
+            tile[ee][i - ee * READS] = keep ? src[i] * scale : 0.f;
         }
         if (tid < READS) {
             const uint8_t c = x[((size_t)b * READS + tid) * COLS + p];
             codes[tid] = c < NCODES ? c : 0;
         }
         __syncthreads();
-        if (e < EMB) {
-            for (int r = rl; r < READS; r += 5) {
-                const unsigned long long i0 = (((unsigned long long)b * READS + r) * COLS + p) * EMB + e;
-                const float v = drop_keep(d, DROP_EMB, i0) ? tile[e][r] * d.scale : 0.f;
-                const int c = codes[r];
+        // stable counting sort: warp w ranks the reads of codes w and w + 8
+        for (int c = warp; c < NCODES; c += TR_THREADS / 32) {
+            int n = 0;
+            for (int r0 = 0; r0 < READS; r0 += 32) {
+                const int r = r0 + lane;
+                n += __popc(__ballot_sync(0xffffffffu, r < READS && codes[r] == c));
+            }
+            if (lane == 0) ccount[c] = n;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int o = 0;
+            for (int c = 0; c < NCODES; ++c) { cbeg[c] = o; o += ccount[c]; }
+            cbeg[NCODES] = o;
+        }
+        __syncthreads();
+        for (int c = warp; c < NCODES; c += TR_THREADS / 32) {
+            int o = cbeg[c];
+            for (int r0 = 0; r0 < READS; r0 += 32) {
+                const int r = r0 + lane;
+                const bool hit = r < READS && codes[r] == c;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (hit) order[o + __popc(m & ((1u << lane) - 1u))] = (uint8_t)r;
+                o += __popc(m);
+            }
+        }
+        __syncthreads();
 #pragma unroll
-                for (int cc = 0; cc < NCODES; ++cc) acc[cc] += (c == cc) ? v : 0.f;
+        for (int i = 0; i < 3; ++i) {
+            const int q = tid + i * TR_THREADS;
+            if (q < NCODES * EMB) {
+                const int c = q / EMB, e = q - c * EMB;
+                float a = acc[i];
+                for (int k = cbeg[c]; k < cbeg[c + 1]; ++k) a += tile[e][order[k]];
+                acc[i] = a;
             }
         }
     }
-    __syncthreads();
-    if (e < EMB) {
 #pragma unroll
-        for (int c = 0; c < NCODES; ++c) atomicAdd(&tab[c * EMB + e], acc[c]);
+    for (int i = 0; i < 3; ++i) {
+        const int q = tid + i * TR_THREADS;
+        if (q < NCODES * EMB) atomicAdd(dE + q, acc[i]);
     }
+}
+
+// Bias gradients of one GRU layer, both directions, in one pass over dgi [rows][768] and dghn [rows][256]:
+//   b_ih[d] = colsum(dgi_d)          b_hh[d] = (colsum(dgi_d)[r, z], colsum(dghn_d))
+__global__ void __launch_bounds__(TR_THREADS)
+gru_bias_grad_kernel(const float* __restrict__ dgi, const float* __restrict__ dghn, int rows,
+                     float* __restrict__ bih0, float* __restrict__ bhh0, float* __restrict__ bih1,
+                     float* __restrict__ bhh1) {
+    __shared__ float part[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cl;                  // 0..767 dgi, 768..1023 dghn
+    const bool from_gi = col < GI_N;
+    const float* src = from_gi ? dgi + col : dghn + (col - GI_N);
+    const int ld = from_gi ? GI_N : OUT_W;
+    float acc = 0.f;
+    for (int m = blockIdx.y * 8 + rl; m < rows; m += gridDim.y * 8) acc += src[(size_t)m * ld];
+    part[rl][cl] = acc;
     __syncthreads();
-    for (int i = tid; i < NCODES * EMB; i += TR_THREADS) atomicAdd(dE + i, tab[i]);
+    if (rl == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][cl];
+        if (from_gi) {
+            const int d = col / G3, q = col - d * G3;
+            atomicAdd((d ? bih1 : bih0) + q, t);
+            if (q < 2 * HID) atomicAdd((d ? bhh1 : bhh0) + q, t);
+        } else {
+            const int c = col - GI_N, d = c / HID, jj = c - d * HID;
+            atomicAdd((d ? bhh1 : bhh0) + 2 * HID + jj, t);
+        }
+    }
 }
 
 static int grid_for(size_t n, int cap) {
@@ -209,10 +278,10 @@ static int grid_for(size_t n, int cap) {
     return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
 }
 
-cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, int nwin, DropCfg d, int* status,
-                              cudaStream_t s) {
+cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, int nwin, DropCfg d,
+                              int* status, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
-    embed_drop_kernel<<<nwin * COLS, TR_THREADS, 0, s>>>(x, E, ep, d, status);
+    embed_drop_kernel<<<nwin * COLS, TR_THREADS, 0, s>>>(x, E, ep, bits, d, status);
     return cudaGetLastError();
 }
 
@@ -252,12 +321,21 @@ cudaError_t launch_colsum(const float* A, int lda, int rows, int ncols, float* o
     return cudaGetLastError();
 }
 
-cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, float* dE, int nwin, DropCfg d, int num_sms,
-                              cudaStream_t s) {
+cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, const uint32_t* bits, float* dE, int nwin,
+                              float scale, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
     const int nbp = nwin * COLS;
     const int grid = nbp < 2 * num_sms ? nbp : 2 * num_sms;
-    embed_grad_kernel<<<grid, TR_THREADS, 0, s>>>(dep, x, dE, nwin, d);
+    embed_grad_kernel<<<grid, TR_THREADS, 0, s>>>(dep, x, bits, dE, nwin, scale);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gru_bias_grad(const float* dgi, const float* dghn, int rows, float* bih0, float* bhh0,
+                                 float* bih1, float* bhh1, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    int gy = (rows + 63) / 64;
+    if (gy > 64) gy = 64;
+    gru_bias_grad_kernel<<<dim3((GI_N + OUT_W) / 32, gy), TR_THREADS, 0, s>>>(dgi, dghn, rows, bih0, bhh0, bih1, bhh1);
     return cudaGetLastError();
 }
 

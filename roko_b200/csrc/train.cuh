@@ -45,16 +45,19 @@ struct GemmArgs {
 cudaError_t launch_gemm(GemmArgs g, bool ka, bool kb, int epi, int splits, int num_sms, cudaStream_t s);
 
 // ---- element-wise / small kernels (train.cu) -----------------------------------------------------
-cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, int nwin, DropCfg d, int* status,
-                              cudaStream_t s);
+constexpr int MASK_WORDS = 320;          // keep bits of one (window, column)'s 10 000 embedding outputs (313 words used)
+cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, int nwin, DropCfg d,
+                              int* status, cudaStream_t s);
 cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, float* u, int rows50, DropCfg d,
                            cudaStream_t s);
 cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2,
                            int rows50, float scale, int num_sms, cudaStream_t s);
 cudaError_t launch_drop_apply(const float* in, float* out, size_t n, unsigned int site, DropCfg d, cudaStream_t s);
 cudaError_t launch_colsum(const float* A, int lda, int rows, int ncols, float* out, cudaStream_t s);
-cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, float* dE, int nwin, DropCfg d, int num_sms,
-                              cudaStream_t s);
+cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, const uint32_t* bits, float* dE, int nwin,
+                              float scale, int num_sms, cudaStream_t s);
+cudaError_t launch_gru_bias_grad(const float* dgi, const float* dghn, int rows, float* bih0, float* bhh0,
+                                 float* bih1, float* bhh1, cudaStream_t s);
 cudaError_t launch_drop_mask(unsigned int site, size_t n, uint8_t* out, DropCfg d, cudaStream_t s);
 
 // ---- recurrence (rec.cu forward with gate saving, rec_bwd.cu) -------------------------------------

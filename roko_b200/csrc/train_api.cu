@@ -30,10 +30,11 @@ constexpr int TRAIN_MAX_WINDOWS = 1024;
 constexpr size_t ROW_EP = (size_t)EMB * READS;       // per (window, column) row
 constexpr size_t ROW_A1 = (size_t)EMB * FC1;
 constexpr size_t ROW_FLOATS = ROW_EP + ROW_A1 + IN0P + GI_N + 3 * (2 * HID * 4) + 3 * OUT_W + 2 * OUT_W
-                              + GI_N + OUT_W + OUT_W + IN0P;
+                              + GI_N + OUT_W + OUT_W + IN0P + MASK_WORDS;
 
 struct TrainWs {
     float *ep, *a1, *u, *gi, *gates[3], *out[3], *outd[2], *dghp, *dghn, *dh, *din;
+    uint32_t* bits;
 };
 
 TrainWs carve(void* base, size_t rows) {
@@ -50,6 +51,7 @@ TrainWs carve(void* base, size_t rows) {
     w.dghn = p; p += rows * OUT_W;
     w.dh = p; p += rows * OUT_W;
     w.din = p; p += rows * IN0P;
+    w.bits = reinterpret_cast<uint32_t*>(p);
     return w;
 }
 
@@ -100,7 +102,7 @@ int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows,
     const float* pk = m->packed;
 
     TCU(cudaMemsetAsync(w.u, 0, (size_t)rows * IN0P * sizeof(float), s));      // the 12 pad columns stay zero
-    TCU(launch_embed_drop(x, raw + RAW_E, w.ep, n_windows, d, m->status, s));
+    TCU(launch_embed_drop(x, raw + RAW_E, w.ep, w.bits, n_windows, d, m->status, s));
     {   // a1 = dropout(relu(ep W1^T + b1))                                     rnn_model.py:50-51
         GemmArgs a{};
         a.A = w.ep; a.lda = READS; a.B = raw + RAW_W1; a.ldb = READS; a.C = w.a1; a.ldc = FC1;
@@ -163,10 +165,9 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
             b.A = w.dghp + dir * G3; b.lda = GI_N; b.B = w.out[l] + dir * HID; b.ldb = OUT_W;
             b.C = grad_raw + raw_whh(l, dir); b.ldc = HID; b.M = G3; b.N = HID; b.K = rows;
             TCU(launch_gemm(b, false, false, EPI_ATOMIC, 0, sms, s));
-            TCU(launch_colsum(dgi + dir * G3, GI_N, rows, G3, grad_raw + raw_bih(l, dir), s));
-            TCU(launch_colsum(dgi + dir * G3, GI_N, rows, 2 * HID, grad_raw + raw_bhh(l, dir), s));
-            TCU(launch_colsum(w.dghn + dir * HID, OUT_W, rows, HID, grad_raw + raw_bhh(l, dir) + 2 * HID, s));
         }
+        TCU(launch_gru_bias_grad(dgi, w.dghn, rows, grad_raw + raw_bih(l, 0), grad_raw + raw_bhh(l, 0),
+                                 grad_raw + raw_bih(l, 1), grad_raw + raw_bhh(l, 1), s));
         for (int dir = 0; dir < 2; ++dir) {               // d(in) = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd
             GemmArgs a{};
             a.A = dgi + dir * G3; a.lda = GI_N; a.B = raw + raw_wih(l, dir); a.ldb = in_w; a.C = w.din; a.ldc = in_ld;
@@ -188,7 +189,7 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         b.A = w.a1; b.lda = FC1; b.B = raw + RAW_W1; b.ldb = READS; b.C = w.ep; b.ldc = READS;
         b.M = rows50; b.N = READS; b.K = FC1;
         TCU(launch_gemm(b, true, false, EPI_STORE, 1, sms, s));
-        TCU(launch_embed_grad(w.ep, x, grad_raw + RAW_E, n_windows, d, sms, s));
+        TCU(launch_embed_grad(w.ep, x, w.bits, grad_raw + RAW_E, n_windows, d.scale, sms, s));
     }
     return ROKO_B200_OK;
 }

@@ -26,11 +26,14 @@ class File:
 
 
 def register(path, contigs, groups):
-    """contigs: {name: seq};  groups: [(group_name, contig, positions (N,90,2) i64, examples (N,200,90) u8)]"""
+    """contigs: {name: seq};  groups: [(group_name, contig, positions (N,90,2) i64, examples (N,200,90) u8
+    [, labels (N,90)])] -- the 5-tuple form is a training file (reference data.py:40-48)."""
     root = {"contigs": _Group()}
     for name, seq in contigs.items():
         root["contigs"][name] = _Group({"name": name, "seq": seq, "len": len(seq)})
-    for gname, contig, pos, ex in groups:
+    for gname, contig, pos, ex, *rest in groups:
         root[gname] = _Group({"contig": contig, "size": len(ex)}, positions=np.asarray(pos, np.int64),
                              examples=np.asarray(ex, np.uint8))
+        if rest:
+            root[gname]["labels"] = np.asarray(rest[0], np.int64)
     _FILES[path] = root

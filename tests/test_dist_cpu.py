@@ -77,3 +77,67 @@ def test_broadcast_and_gather_world2(n_total):
     for same, nbytes, ok, shape in res:
         assert same and ok and nbytes == 1099731 * 4
     assert any(shape == (n_total, 90) for _, _, _, shape in res)
+
+
+def _train_worker(rank, world, port, outdir, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import roko_b200.dist as rd
+        from roko_b200 import train as T
+        from roko_b200.synth import structured_windows
+        from tests import fake_h5
+        from tests.test_train_host import TinyModel
+
+        # (1) average_gradients: mean over ranks, parameters without a local gradient count as zeros
+        torch.manual_seed(7)
+        m = TinyModel()
+        m.fc.weight.grad = torch.full_like(m.fc.weight, float(rank + 1))
+        if rank == 0:
+            m.fc.bias.grad = torch.full_like(m.fc.bias, 4.0)
+        nbytes = rd.average_gradients(m)
+        ok_avg = bool(torch.allclose(m.fc.weight.grad, torch.full_like(m.fc.weight, 1.5))
+                      and torch.allclose(m.fc.bias.grad, torch.full_like(m.fc.bias, 2.0)))
+
+        # (2) two ranks training on halves of every batch == one process training on whole batches
+        x, y = structured_windows(32, seed=21, return_truth=True)
+        pos = np.zeros((32, 90, 2), np.int64)
+        fake_h5.register("mem://dist_train", {"c": "ACGT"}, [("c_0", "c", pos, x, y)])
+        torch.manual_seed(100 + rank)                     # different initial weights: rank 0's must win
+        model = TinyModel()
+        hist = T.train("mem://dist_train", outdir, "mem://dist_train", mem=True, batch_size=8, epochs=2, lr=1e-2,
+                       model=model, device="cpu", h5=fake_h5, log=lambda *_: None, seed=5)
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        q.put((rank, ok_avg, nbytes, flat.numpy(), hist["checkpoint"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_world2(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res) and res[0][2] == (5 * 12 + 5) * 4
+    assert np.allclose(res[0][3], res[1][3], atol=1e-7)          # ranks stay in lock step
+    assert res[0][4] is not None and res[1][4] is None            # rank 0 alone writes checkpoints
+
+    # single-process run from rank 0's start: mean of the two half-batch gradients == whole-batch gradient
+    from roko_b200 import train as T
+    from roko_b200.synth import structured_windows
+    from tests import fake_h5
+    from tests.test_train_host import TinyModel
+    x, y = structured_windows(32, seed=21, return_truth=True)
+    fake_h5.register("mem://dist_train", {"c": "ACGT"}, [("c_0", "c", np.zeros((32, 90, 2), np.int64), x, y)])
+    torch.manual_seed(100)
+    model = TinyModel()
+    T.train("mem://dist_train", str(tmp_path / "single"), None, mem=True, batch_size=8, epochs=2, lr=1e-2,
+            model=model, device="cpu", h5=fake_h5, log=lambda *_: None, seed=5)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).numpy()
+    assert np.allclose(flat, res[0][3], atol=2e-5)

@@ -170,3 +170,25 @@ def test_training_errors(train_model, train_golden):
     train_model(bad)
     with pytest.raises(IndexError):
         train_model.check_codes()
+
+
+def test_train_driver_end_to_end(tmp_path):
+    """roko_b200.train.train (the reference's train.py entry point) on the real model: labelled windows
+    from an in-memory .hdf5 stand-in, two epochs, checkpoint interchangeable with the reference's."""
+    from roko_b200 import train as T
+    from tests import fake_h5
+    xs, ys = structured_windows(96, seed=33, return_truth=True)
+    pos = np.zeros((96, 90, 2), np.int64)
+    fake_h5.register("mem://gpu_train", {"c": "ACGT"}, [("c_0", "c", pos[:64], xs[:64], ys[:64])])
+    fake_h5.register("mem://gpu_val", {"c": "ACGT"}, [("c_1", "c", pos[64:], xs[64:], ys[64:])])
+    logs = []
+    hist = T.train("mem://gpu_train", str(tmp_path), "mem://gpu_val", mem=True, batch_size=16, epochs=3, lr=2e-3,
+                   device="cuda:0", h5=fake_h5, log=logs.append, seed=4)
+    print(hist)
+    assert hist["epochs"] == 3 and hist["checkpoint"]
+    assert hist["train_loss"][-1] < hist["train_loss"][0]
+    assert hist["val_loss"][-1] < 1.6                                   # below ln 5: it learned something
+    sd = torch.load(hist["checkpoint"])
+    assert list(sd) == RM.state_keys()                                   # the reference's state_dict contract
+    m = RM.RNN(RM.IN_SIZE, RM.HIDDEN_SIZE, RM.NUM_LAYERS)
+    m.load_state_dict(sd, strict=True)

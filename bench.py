@@ -410,6 +410,11 @@ def run_ours(args):
                           "note": "device-resident, one stream, consecutive steps fused into one pass (what predict_host does); "
                                   "TFLOP/s are algorithmic fp32 FLOPs: the tensor kernels spend 3 tf32 MMAs per product"},
         }
+        if world == 1:
+            tms, _ = train_steps(dev, 128, 20, 3)
+            line["training"] = {"windows_per_s": 128 / (tms * 1e-3), "ms_per_step": tms, "batch": 128,
+                                "note": "roko train.py step (train-mode forward with dropout, cross-entropy, hand-written "
+                                        "backward, Adam) on device-resident synthetic windows; see bench.py --mode train"}
         if world == 1 and not args.no_cpu_baseline:
             wps, cores, sample = cpu_baseline_bounded(15.0, batch)
             line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
@@ -420,8 +425,81 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def train_steps(dev, batch, steps, warmup, world=1, seed=0):
+    """Reference training step (roko/train.py:41-55: train mode, zero_grad, forward, cross-entropy, backward,
+    Adam lr 1e-4) on synthetic labelled windows resident on the device; gradients averaged over ranks with one
+    flat all-reduce when world > 1.  Returns (ms per step from CUDA events, last loss)."""
+    import torch
+    import torch.nn.functional as F
+    from roko_b200 import dist as rdist
+    from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+    torch.manual_seed(seed)
+    model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(dev).train()
+    if world > 1:
+        rdist.broadcast_weights(model, src=0)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator(device=dev).manual_seed(77 + seed)
+    pool = 8                                                   # 8 x 2.3 MB inputs; activations (1 GB) dwarf L2 anyway
+    xs = torch.randint(0, 12, (pool, batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)
+    ys = torch.randint(0, 5, (pool, batch, COLS), dtype=torch.int64, device=dev, generator=g)
+    beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loss = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            beg.record()
+        model.zero_grad()
+        loss = F.cross_entropy(model(xs[i % pool]).transpose(1, 2), ys[i % pool])
+        loss.backward()
+        if world > 1:
+            rdist.average_gradients(model)
+        opt.step()
+    end.record()
+    torch.cuda.synchronize()
+    return beg.elapsed_time(end) / steps, float(loss.item())
+
+
+def run_train(args):
+    """bench.py --mode train: BASELINE.json config 5 (training), weak scaling, one JSON line on rank 0."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode train needs a B200: the training kernels are CUDA only")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = min(args.steps, 200), max(3, args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, loss = train_steps(dev, args.batch, K, W, world, seed=rank)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        print(json.dumps({
+            "metric": "train_windows_per_s", "value": args.batch * world / (ms * 1e-3), "unit": "windows/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "roko train.py step: RNN(500,128,3) train mode (dropout 0.2), cross-entropy, backward, Adam 1e-4; "
+                                   "x = (batch,200,90) u8 uniform codes, y uniform labels, device resident",
+                       "batch_per_gpu": args.batch, "parallelism": f"dp{world}",
+                       "collectives": "one flat 4.4 MB gradient all-reduce per step" if world > 1 else "none (1 GPU)"},
+            "last_loss": loss, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: the north-star hot path (default, the driver's contract); train: the training step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
@@ -435,6 +513,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

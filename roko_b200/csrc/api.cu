@@ -153,6 +153,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     m->num_sms = prop.multiProcessorCount;
     cudaError_t e = cudaMalloc(&m->packed, (size_t)PK_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->raw_stage, (size_t)RAW_TOTAL * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->raw_al, (size_t)(RAW_TOTAL + RAW_AL_PAD) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
     if (e == cudaSuccess) e = front_setup();
@@ -184,6 +185,9 @@ int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CU(cudaMemcpyAsync(m->raw_stage, raw, (size_t)RAW_TOTAL * sizeof(float),
                        raw_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(m->raw_al, m->raw_stage, (size_t)RAW_GRU * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(m->raw_al + RAW_GRU + RAW_AL_PAD, m->raw_stage + RAW_GRU,
+                       (size_t)(RAW_TOTAL - RAW_GRU) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(launch_pack(m->raw_stage, m->packed, s));
     // W2 / b1 / b2 ride in the front-end kernel's parameter bank: keep a host copy
     if (raw_on_device) {
@@ -208,7 +212,7 @@ int roko_b200_model_destroy(roko_b200_model* m) {
         if (sl.done) cudaEventDestroy(sl.done);
         cudaFree(sl.x); cudaFree(sl.labels); cudaFree(sl.logits); cudaFree(sl.ws);
     }
-    cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->status);
+    cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->raw_al); cudaFree(m->status);
     delete m;
     return ROKO_B200_OK;
 }

@@ -12,6 +12,7 @@ struct roko_b200_model {
     int num_sms = 148;
     float* packed = nullptr;
     float* raw_stage = nullptr;     // device copy of the raw (state_dict order) weights; the training backward reads them
+    float* raw_al = nullptr;        // the same with 2 floats of padding before the GRU section: every tensor 16-byte aligned
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
     int use_tc = 3;                 // projection: 3 = persistent tcgen05, double-buffered accumulators (proj_tc3.cu, default);
@@ -29,6 +30,11 @@ struct roko_b200_model {
     } slot[NSLOT];
     int slot_cap = 0;
 };
+
+// offset of raw element `off` inside raw_al (RAW_GRU is 2 mod 4 and every later tensor size is a multiple of 4)
+constexpr int RAW_AL_PAD = 2;
+static_assert((roko::RAW_GRU + RAW_AL_PAD) % 4 == 0 && roko::RAW_W1 % 4 == 0 && roko::RAW_W2 % 4 == 0, "raw_al alignment");
+__host__ __device__ constexpr int raw_al_off(int off) { return off >= roko::RAW_GRU ? off + RAW_AL_PAD : off; }
 
 // Input projection of GRU layer `l` with the kernel the model is configured for (see use_tc).
 inline cudaError_t proj_dispatch(const roko_b200_model* m, const float* in, int l, float* gi, int rows,

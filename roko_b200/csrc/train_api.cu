@@ -170,7 +170,7 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
                                  grad_raw + raw_bih(l, 1), grad_raw + raw_bhh(l, 1), s));
         for (int dir = 0; dir < 2; ++dir) {               // d(in) = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd
             GemmArgs a{};
-            a.A = dgi + dir * G3; a.lda = GI_N; a.B = raw + raw_wih(l, dir); a.ldb = in_w; a.C = w.din; a.ldc = in_ld;
+            a.A = dgi + dir * G3; a.lda = GI_N; a.B = m->raw_al + raw_al_off(raw_wih(l, dir)); a.ldb = in_w; a.C = w.din; a.ldc = in_ld;
             a.M = rows; a.N = in_w; a.K = G3;
             TCU(launch_gemm(a, true, false, dir == 0 ? EPI_STORE : EPI_ACC, 1, sms, s));
         }

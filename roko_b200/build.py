@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libroko_b200.so")
 OBJ = os.path.join(CSRC, "build")
 SOURCES = ["pack.cu", "front.cu", "proj.cu", "proj_tc.cu", "proj_tc2.cu", "proj_tc3.cu", "rec.cu", "rec_tc.cu", "head.cu", "api.cu",
-           "gemm.cu", "train.cu", "rec_bwd.cu", "train_api.cu"]
+           "gemm.cu", "train.cu", "train_tc.cu", "rec_bwd.cu", "train_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

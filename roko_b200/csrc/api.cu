@@ -8,6 +8,7 @@
 
 #include "../../include/roko_b200.h"
 #include "model.h"
+#include "train.cuh"
 
 using namespace roko;
 
@@ -154,6 +155,9 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     cudaError_t e = cudaMalloc(&m->packed, (size_t)PK_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->raw_stage, (size_t)RAW_TOTAL * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->raw_al, (size_t)(RAW_TOTAL + RAW_AL_PAD) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->train_img, train_tc_image_floats() * sizeof(float));
+    if (e == cudaSuccess) e = train_tc_setup();
+    if (const char* tt = getenv("ROKO_B200_TRAIN_TC")) m->train_tc = atoi(tt);
     if (e == cudaSuccess) e = cudaMalloc(&m->status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
     if (e == cudaSuccess) e = front_setup();
@@ -212,7 +216,7 @@ int roko_b200_model_destroy(roko_b200_model* m) {
         if (sl.done) cudaEventDestroy(sl.done);
         cudaFree(sl.x); cudaFree(sl.labels); cudaFree(sl.logits); cudaFree(sl.ws);
     }
-    cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->raw_al); cudaFree(m->status);
+    cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->raw_al); cudaFree(m->train_img); cudaFree(m->status);
     delete m;
     return ROKO_B200_OK;
 }

@@ -60,6 +60,14 @@ cudaError_t launch_gru_bias_grad(const float* dgi, const float* dghn, int rows, 
                                  float* bih1, float* bhh1, cudaStream_t s);
 cudaError_t launch_drop_mask(unsigned int site, size_t n, uint8_t* out, DropCfg d, cudaStream_t s);
 
+// ---- row-streaming front-end products on tcgen05 (train_tc.cu) -------------------------------------
+size_t train_tc_image_floats();
+cudaError_t train_tc_setup();
+cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s);
+cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, float* a1, int rows, DropCfg d,
+                          int num_sms, cudaStream_t s);
+cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s);
+
 // ---- recurrence (rec.cu forward with gate saving, rec_bwd.cu) -------------------------------------
 // gates: [row][dir][j] float4 (r, z, n, W_hn h + b_hn)
 cudaError_t launch_rec_train(const float* gi, const float* whh_d0, size_t dir_stride, const float* bhn_d0,

@@ -103,7 +103,10 @@ int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows,
 
     TCU(cudaMemsetAsync(w.u, 0, (size_t)rows * IN0P * sizeof(float), s));      // the 12 pad columns stay zero
     TCU(launch_embed_drop(x, raw + RAW_E, w.ep, w.bits, n_windows, d, m->status, s));
-    {   // a1 = dropout(relu(ep W1^T + b1))                                     rnn_model.py:50-51
+    if (m->train_tc) {   // a1 = dropout(relu(ep W1^T + b1))                     rnn_model.py:50-51
+        TCU(launch_train_images(raw + RAW_W1, m->train_img, s));
+        TCU(launch_fc1_tc(w.ep, m->train_img, raw + RAW_B1, w.a1, rows50, d, m->num_sms, s));
+    } else {
         GemmArgs a{};
         a.A = w.ep; a.lda = READS; a.B = raw + RAW_W1; a.ldb = READS; a.C = w.a1; a.ldc = FC1;
         a.M = rows50; a.N = FC1; a.K = READS; a.bias = raw + RAW_B1; a.drop = d;
@@ -185,10 +188,14 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         a.M = FC1; a.N = READS; a.K = rows50;
         TCU(launch_gemm(a, false, false, EPI_ATOMIC, 0, sms, s));
         TCU(launch_colsum(w.a1, FC1, rows50, FC1, grad_raw + RAW_B1, s));
-        GemmArgs b{};                                     // dep = dap W1 (over ep, which nothing reads any more)
-        b.A = w.a1; b.lda = FC1; b.B = raw + RAW_W1; b.ldb = READS; b.C = w.ep; b.ldc = READS;
-        b.M = rows50; b.N = READS; b.K = FC1;
-        TCU(launch_gemm(b, true, false, EPI_STORE, 1, sms, s));
+        if (m->train_tc) {                                // dep = dap W1 (over ep, which nothing reads any more)
+            TCU(launch_dep_tc(w.a1, m->train_img, w.ep, rows50, sms, s));
+        } else {
+            GemmArgs b{};
+            b.A = w.a1; b.lda = FC1; b.B = raw + RAW_W1; b.ldb = READS; b.C = w.ep; b.ldc = READS;
+            b.M = rows50; b.N = READS; b.K = FC1;
+            TCU(launch_gemm(b, true, false, EPI_STORE, 1, sms, s));
+        }
         TCU(launch_embed_grad(w.ep, x, w.bits, grad_raw + RAW_E, n_windows, d.scale, sms, s));
     }
     return ROKO_B200_OK;

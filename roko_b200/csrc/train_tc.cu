@@ -1,0 +1,336 @@
+// The two row-streaming products of the training front end on tcgen05 (reference ops: fc1 of
+// roko/rnn_model.py:50 in train mode, and the d(embedding output) product of its backward):
+//     fc1 :  a1[row][j]  = dropout(relu(b1[j] + sum_r ep[row][r] W1[j][r]))      row = (window, column, channel)
+//     dep :  dep[row][r] = sum_j dap[row][j] W1[j][r]
+// 576 000 rows per 128-window batch, 0.46 GB in or out each: the kernels stream 128-row blocks of the
+// row-major operand through the producer warps (fp32 -> tf32 hi / lo images, K-major SWIZZLE_128B) while the
+// small weight operand arrives as pre-split images by bulk copy; 3xTF32 accumulation in TMEM, two accumulators
+// so the epilogue of block i overlaps the MMAs of block i+1.  Same machinery as proj_tc3.cu (which see for the
+// descriptor and barrier conventions), templated on the tile width, the K extent and the epilogue.
+#include "train.cuh"
+
+namespace roko {
+
+constexpr int T_THREADS = 320;
+constexpr int T_BM = 128, T_BK = 32;
+constexpr int T_A_IMG = T_BM * T_BK * 4;               // 16 KB
+constexpr int T_EPI_ROW = 36;
+constexpr int T_EPI_BYTES = 4 * 32 * T_EPI_ROW * 4;
+__host__ __device__ constexpr int t_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
+__host__ __device__ constexpr int t_smem_bytes(int bn) { return 2 * t_stage_bytes(bn) + 1024 + 256 + T_EPI_BYTES; }
+
+__device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void t_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void t_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t t_make_desc(uint32_t saddr) {      // K-major SWIZZLE_128B, SBO 1024 B
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void t_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ uint32_t t_elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e;
+}
+__device__ __forceinline__ void t_umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float t_tf32_hi(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+enum { TEPI_STORE = 0, TEPI_FC1 = 1 };
+
+// C[m][0..NREAL) (row stride NREAL) = epilogue(A[m][0..KREAL) (row stride LDA) x W), W as KB pairs of
+// hi / lo images of BN rows x 32 floats; rows >= NREAL and columns >= KREAL of the images are zero.
+template <int BN, int KB, int LDA, int KREAL, int NREAL, int EPI>
+__global__ void __launch_bounds__(T_THREADS, 1)
+tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const float* __restrict__ bias,
+                 float* __restrict__ C, int M, int ntiles, DropCfg drop) {
+    static_assert(KREAL % 4 == 0 && NREAL % 4 == 0 && LDA % 4 == 0 && KB * T_BK >= KREAL && BN >= NREAL && 2 * BN <= 512, "shape");
+    constexpr int W_IMG = BN * T_BK * 4;
+    constexpr int STAGE = t_stage_bytes(BN);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
+    extern __shared__ unsigned char t_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* epi_stage = reinterpret_cast<float*>(smem + 2 * STAGE + 256);
+    const uint32_t sbase = t_smem_u32(smem);
+    const uint32_t bar0 = t_smem_u32(bars);
+    // barriers: full_a[s] = s, full_w[s] = 2+s, empty[s] = 4+s, acc_full[b] = 6+b, acc_empty[b] = 8+b
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            t_mbar_init(BAR(s), 128);
+            t_mbar_init(BAR(2 + s), 1);
+            t_mbar_init(BAR(4 + s), 1);
+            t_mbar_init(BAR(6 + s), 1);
+            t_mbar_init(BAR(8 + s), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------- A producers ----------------------------------------------
+        const int chunk = tid & 7, rr = tid >> 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = tile * T_BM;
+            const float* arow[8];
+            bool valid[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rr + 16 * i;
+                valid[i] = (m0 + r) < M;
+                arow[i] = A + (size_t)(valid[i] ? m0 + r : 0) * LDA + chunk * 4;
+            }
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v[i] = (valid[i] && chunk * 4 < KREAL) ? __ldg(reinterpret_cast<const float4*>(arow[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it & 1;
+                t_mbar_wait(BAR(4 + s), ((it >> 1) & 1) ^ 1);
+                unsigned char* ahi = smem + s * STAGE;
+                unsigned char* alo = ahi + T_A_IMG;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rr + 16 * i;
+                    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+                    float4 h, l;
+                    h.x = t_tf32_hi(v[i].x); l.x = v[i].x - h.x;
+                    h.y = t_tf32_hi(v[i].y); l.y = v[i].y - h.y;
+                    h.z = t_tf32_hi(v[i].z); l.z = v[i].z - h.z;
+                    h.w = t_tf32_hi(v[i].w); l.w = v[i].w - h.w;
+                    *reinterpret_cast<float4*>(ahi + off) = h;
+                    *reinterpret_cast<float4*>(alo + off) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                t_mbar_arrive(BAR(s));
+                if (kb + 1 < KB) {
+                    const bool kin = (kb + 1) * T_BK + chunk * 4 < KREAL;      // the last k block may be partly padding
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        v[i] = (valid[i] && kin) ? __ldg(reinterpret_cast<const float4*>(arow[i] + (kb + 1) * T_BK))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------- W loader (bulk copies) -------------------------------------
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it & 1;
+                    t_mbar_wait(BAR(4 + s), ((it >> 1) & 1) ^ 1);
+                    t_mbar_expect_tx(BAR(2 + s), 2 * W_IMG);
+                    t_bulk_g2s(sbase + s * STAGE + 2 * T_A_IMG, wimg + (size_t)kb * 2 * (W_IMG / 4), 2 * W_IMG, BAR(2 + s));
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------- MMA issuer (whole warp, uniform) ---------------------------
+        if (tmem_d != 0) __trap();                                 // all 512 columns are ours -> base 0
+        const uint32_t elected = t_elect_one();
+        int it = 0, j = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+            const uint32_t buf = j & 1;
+            t_mbar_wait(BAR(8 + buf), ((j >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = buf * BN;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                t_mbar_wait(BAR(s), ph);
+                t_mbar_wait(BAR(2 + s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = sbase + s * STAGE, a_lo = a_hi + T_A_IMG;
+                const uint32_t w_hi = a_lo + T_A_IMG, w_lo = w_hi + W_IMG;
+#pragma unroll
+                for (int kk = 0; kk < T_BK / 8; ++kk) {
+                    const uint64_t dah = t_make_desc(a_hi + kk * 32), dal = t_make_desc(a_lo + kk * 32);
+                    const uint64_t dwh = t_make_desc(w_hi + kk * 32), dwl = t_make_desc(w_lo + kk * 32);
+                    t_umma_tf32(d, dal, dwh, IDESC, (kb | kk) ? 1u : 0u, elected);   // small terms first
+                    t_umma_tf32(d, dah, dwl, IDESC, 1u, elected);
+                    t_umma_tf32(d, dah, dwh, IDESC, 1u, elected);
+                }
+                if (elected) t_umma_commit(BAR(4 + s));
+                __syncwarp();
+            }
+            if (elected) t_umma_commit(BAR(6 + buf));
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------- epilogue warps (6..9) -------------------------------------
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may read
+        int j = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+            const uint32_t buf = j & 1;
+            const int m0 = tile * T_BM;
+            t_mbar_wait(BAR(6 + buf), (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * BN;
+            float* T = epi_stage + (warp - 6) * 32 * T_EPI_ROW;
+            const int rsub = lane >> 3, csub = (lane & 7) * 4;      // read-back role: 4 rows x 8 float4 per instruction
+#pragma unroll 1
+            for (int c0 = 0; c0 < NREAL; c0 += 32) {
+                uint32_t r[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq)
+                    *reinterpret_cast<float4*>(T + lane * T_EPI_ROW + qq * 4) =
+                        make_float4(__uint_as_float(r[qq * 4 + 0]), __uint_as_float(r[qq * 4 + 1]),
+                                    __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
+                __syncwarp();
+                const int n = c0 + csub;                             // first of this lane's 4 columns
+                if (n < NREAL) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EPI == TEPI_FC1) b = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {                 // rows 4*it .. 4*it+3, 32 columns, whole row segments
+                        const int rr = it * 4 + rsub;
+                        const int m = m0 + q * 32 + rr;
+                        float4 v = *reinterpret_cast<const float4*>(T + rr * T_EPI_ROW + csub);
+                        if (EPI == TEPI_FC1) {
+                            const unsigned long long e0 = (unsigned long long)m * NREAL + n;
+                            v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f);
+                            v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+                            v.x = drop_keep(drop, DROP_FC1, e0) ? v.x * drop.scale : 0.f;
+                            v.y = drop_keep(drop, DROP_FC1, e0 + 1) ? v.y * drop.scale : 0.f;
+                            v.z = drop_keep(drop, DROP_FC1, e0 + 2) ? v.z * drop.scale : 0.f;
+                            v.w = drop_keep(drop, DROP_FC1, e0 + 3) ? v.w * drop.scale : 0.f;
+                        }
+                        if (m < M) *reinterpret_cast<float4*>(C + (size_t)m * NREAL + n) = v;
+                    }
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            t_mbar_arrive(BAR(8 + buf));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512) : "memory");
+    }
+}
+
+// ---- weight images -------------------------------------------------------------------------------------
+// fc1: rows n = j (128, 100 real), k = r (7 blocks of 32, 200 real):  W1[j][r]
+// dep: rows n = r (256, 200 real), k = j (4 blocks of 32, 100 real):  W1[j][r]
+constexpr int FC1_BN = 128, FC1_KB = 7, DEP_BN = 256, DEP_KB = 4;
+constexpr int IMG_FC1_FLOATS = FC1_KB * 2 * FC1_BN * T_BK;        // 57 344
+constexpr int IMG_DEP_FLOATS = DEP_KB * 2 * DEP_BN * T_BK;        // 65 536
+
+__global__ void train_images_kernel(const float* __restrict__ W1, float* __restrict__ img) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= IMG_FC1_FLOATS + IMG_DEP_FLOATS) return;
+    const bool dep = p >= IMG_FC1_FLOATS;
+    int i = dep ? p - IMG_FC1_FLOATS : p;
+    const int img_floats = (dep ? DEP_BN : FC1_BN) * T_BK;
+    const int kb = i / (2 * img_floats);
+    i %= 2 * img_floats;
+    const int half = i / img_floats;
+    const int ob = (i % img_floats) * 4;                             // byte offset inside the image
+    const int rgrp = ob / 1024, within = ob % 1024;
+    const int r8 = within / 128, pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+    const int n = rgrp * 8 + r8;
+    const int k = kb * T_BK + ((pchunk ^ r8) * 4) + w4;              // undo the 128-byte swizzle
+    float v = 0.f;
+    if (!dep) { if (n < FC1 && k < READS) v = W1[n * READS + k]; }
+    else      { if (n < READS && k < FC1) v = W1[k * READS + n]; }
+    const float hi = t_tf32_hi(v);
+    img[p] = half == 0 ? hi : v - hi;
+}
+
+size_t train_tc_image_floats() { return (size_t)IMG_FC1_FLOATS + IMG_DEP_FLOATS; }
+
+cudaError_t train_tc_setup() {
+    cudaError_t e = cudaFuncSetAttribute(tc_stream_kernel<FC1_BN, FC1_KB, READS, READS, FC1, TEPI_FC1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(FC1_BN));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
+}
+
+cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s) {
+    const int n = IMG_FC1_FLOATS + IMG_DEP_FLOATS;
+    train_images_kernel<<<(n + 255) / 256, 256, 0, s>>>(W1, img);
+    return cudaGetLastError();
+}
+
+// a1 = dropout(relu(ep W1^T + b1)):  ep [rows][200] -> a1 [rows][100]
+cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, float* a1, int rows, DropCfg d,
+                          int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int ntiles = (rows + T_BM - 1) / T_BM;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    tc_stream_kernel<FC1_BN, FC1_KB, READS, READS, FC1, TEPI_FC1>
+        <<<grid, T_THREADS, t_smem_bytes(FC1_BN), s>>>(ep, img, b1, a1, rows, ntiles, d);
+    return cudaGetLastError();
+}
+
+// dep = dap W1:  dap [rows][100] -> dep [rows][200]
+cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int ntiles = (rows + T_BM - 1) / T_BM;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    DropCfg none{0ull, 0u, 1.f};
+    tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>
+        <<<grid, T_THREADS, t_smem_bytes(DEP_BN), s>>>(dap, img + IMG_FC1_FLOATS, nullptr, dep, rows, ntiles, none);
+    return cudaGetLastError();
+}
+
+}  // namespace roko

@@ -67,6 +67,7 @@ cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s);
 cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, float* a1, int rows, DropCfg d,
                           int num_sms, cudaStream_t s);
 cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s);
+cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s);
 
 // ---- recurrence (rec.cu forward with gate saving, rec_bwd.cu) -------------------------------------
 // gates: [row][dir][j] float4 (r, z, n, W_hn h + b_hn)

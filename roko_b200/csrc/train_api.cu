@@ -183,10 +183,14 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
     // front end: fc2, fc1, embedding
     TCU(launch_fc2_bwd(w.din, w.u, w.a1, raw + RAW_W2, grad_raw + RAW_W2, grad_raw + RAW_B2, rows50, d.scale, sms, s));
     {
-        GemmArgs a{};                                     // dW1 = dap^T ep
-        a.A = w.a1; a.lda = FC1; a.B = w.ep; a.ldb = READS; a.C = grad_raw + RAW_W1; a.ldc = READS;
-        a.M = FC1; a.N = READS; a.K = rows50;
-        TCU(launch_gemm(a, false, false, EPI_ATOMIC, 0, sms, s));
+        if (m->train_tc >= 2) {                           // dW1 = dap^T ep
+            TCU(launch_dw1_tc(w.a1, w.ep, grad_raw + RAW_W1, rows50, sms, s));
+        } else {
+            GemmArgs a{};
+            a.A = w.a1; a.lda = FC1; a.B = w.ep; a.ldb = READS; a.C = grad_raw + RAW_W1; a.ldc = READS;
+            a.M = FC1; a.N = READS; a.K = rows50;
+            TCU(launch_gemm(a, false, false, EPI_ATOMIC, 0, sms, s));
+        }
         TCU(launch_colsum(w.a1, FC1, rows50, FC1, grad_raw + RAW_B1, s));
         if (m->train_tc) {                                // dep = dap W1 (over ep, which nothing reads any more)
             TCU(launch_dep_tc(w.a1, m->train_img, w.ep, rows50, sms, s));

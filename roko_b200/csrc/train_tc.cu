@@ -267,6 +267,161 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
     }
 }
 
+// ---- dW1 = dap^T ep : a 100 x 200 output reduced over 576 000 rows --------------------------------------
+// Both operands are row-major with the REDUCTION index as the row, i.e. the transpose of what a K-major UMMA
+// operand wants.  Eight producer warps transpose 32-row blocks on the fly: lane = k (row inside the block), one
+// float4 of 4 output rows per task, written as 4 + 4 scalars (tf32 hi / lo) into the swizzled K-major images
+// -- for a fixed output row the 32 lanes fill exactly one 128-byte swizzle row, so the stores are conflict free.
+// Each CTA owns a contiguous range of row blocks, accumulates the whole 128 x 256 (100 x 200 used) tile in TMEM
+// and adds it to global memory once at the end.
+constexpr int DW_THREADS = 288;                        // 8 producer warps (0-3 also epilogue) + 1 MMA warp
+constexpr int DW_BN = 256;
+constexpr int DW_STAGE = 2 * T_A_IMG + 2 * DW_BN * T_BK * 4;     // 96 KB
+constexpr int DW_SMEM = 2 * DW_STAGE + 1024 + 256;
+constexpr int DW_TASKS = FC1 / 4 + READS / 4;          // 25 quads of j + 50 quads of r
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float* __restrict__ dW1, int rows) {
+    constexpr int W_IMG = DW_BN * T_BK * 4;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DW_BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
+    extern __shared__ unsigned char t_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * DW_STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t sbase = t_smem_u32(smem);
+    const uint32_t bar0 = t_smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };       // full[s] = s, empty[s] = 2+s, acc_full = 4
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // this CTA's range of 32-row blocks
+    const int nblocks = (rows + T_BK - 1) / T_BK;
+    const int per = (nblocks + gridDim.x - 1) / gridDim.x;
+    const int kb0 = blockIdx.x * per;
+    const int kb1 = (kb0 + per) < nblocks ? (kb0 + per) : nblocks;
+    const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { t_mbar_init(BAR(s), 256); t_mbar_init(BAR(2 + s), 1); }
+        t_mbar_init(BAR(4), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // image rows the producers never write (j >= 100, r >= 200) feed accumulator rows / columns nobody reads:
+    // zero them once so they at least hold finite numbers
+    for (int i = tid; i < 2 * DW_STAGE / 16; i += DW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------- transposing producers --------------------------------------
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it & 1;
+            const int row = (kb0 + it) * T_BK + lane;              // lane = k inside the block
+            const bool rv = row < rows;
+            float4 v[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const int t = warp + 8 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < DW_TASKS && rv)
+                    v[i] = t < FC1 / 4 ? __ldg(reinterpret_cast<const float4*>(dap + (size_t)row * FC1 + 4 * t))
+                                       : __ldg(reinterpret_cast<const float4*>(ep + (size_t)row * READS + 4 * (t - FC1 / 4)));
+            }
+            t_mbar_wait(BAR(2 + s), ((it >> 1) & 1) ^ 1);
+            unsigned char* st = smem + s * DW_STAGE;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const int t = warp + 8 * i;
+                if (t < DW_TASKS) {
+                    const bool isA = t < FC1 / 4;
+                    unsigned char* hi = st + (isA ? 0 : 2 * T_A_IMG);
+                    unsigned char* lo = hi + (isA ? T_A_IMG : W_IMG);
+                    const int n0 = 4 * (isA ? t : t - FC1 / 4);
+                    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int n = n0 + c;
+                        const int off = (n >> 3) * 1024 + (n & 7) * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4;
+                        const float h = t_tf32_hi(e[c]);
+                        *reinterpret_cast<float*>(hi + off) = h;
+                        *reinterpret_cast<float*>(lo + off) = e[c] - h;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            t_mbar_arrive(BAR(s));
+        }
+    } else {
+        // ------------------------------- MMA issuer (whole warp, uniform) ---------------------------
+        const uint32_t elected = t_elect_one();
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it & 1;
+            t_mbar_wait(BAR(s), (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = sbase + s * DW_STAGE, a_lo = a_hi + T_A_IMG;
+            const uint32_t w_hi = a_lo + T_A_IMG, w_lo = w_hi + W_IMG;
+#pragma unroll
+            for (int kk = 0; kk < T_BK / 8; ++kk) {
+                const uint64_t dah = t_make_desc(a_hi + kk * 32), dal = t_make_desc(a_lo + kk * 32);
+                const uint64_t dwh = t_make_desc(w_hi + kk * 32), dwl = t_make_desc(w_lo + kk * 32);
+                t_umma_tf32(tmem_d, dal, dwh, IDESC, (it | kk) ? 1u : 0u, elected);   // small terms first
+                t_umma_tf32(tmem_d, dah, dwl, IDESC, 1u, elected);
+                t_umma_tf32(tmem_d, dah, dwh, IDESC, 1u, elected);
+            }
+            if (elected) t_umma_commit(BAR(2 + s));
+            __syncwarp();
+        }
+        if (elected) t_umma_commit(BAR(4));
+        __syncwarp();
+    }
+    if (warp < 4 && nkb > 0) {
+        // ------------------------------- epilogue: TMEM -> global adds ------------------------------
+        t_mbar_wait(BAR(4), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int j = warp * 32 + lane;                              // TMEM lane == output row
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < READS; c0 += 32) {
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr + (uint32_t)c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (j < FC1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < READS) atomicAdd(dW1 + j * READS + c0 + i, __uint_as_float(r[i]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(256) : "memory");
+    }
+}
+
+cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int nblocks = (rows + T_BK - 1) / T_BK;
+    const int grid = nblocks < num_sms ? nblocks : num_sms;
+    dw1_tc_kernel<<<grid, DW_THREADS, DW_SMEM, s>>>(dap, ep, dW1, rows);
+    return cudaGetLastError();
+}
+
 // ---- weight images -------------------------------------------------------------------------------------
 // fc1: rows n = j (128, 100 real), k = r (7 blocks of 32, 200 real):  W1[j][r]
 // dep: rows n = r (256, 200 real), k = j (4 blocks of 32, 100 real):  W1[j][r]
@@ -301,8 +456,10 @@ cudaError_t train_tc_setup() {
     cudaError_t e = cudaFuncSetAttribute(tc_stream_kernel<FC1_BN, FC1_KB, READS, READS, FC1, TEPI_FC1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(FC1_BN));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
+    e = cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(dw1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
 }
 
 cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s) {

@@ -7,8 +7,10 @@
 //     dgi = (drp, dzp, dnp)       dgh = (drp, dzp, dq)
 // Same persistent layout as the forward (rec.cu): a CTA is bound to one direction and keeps W_hh
 // (transposed use: 384-long contraction per hidden unit) in registers, 512 threads x 96; thread
-// (j, kq) owns the interleaved slice {16 i + 4 kq + c} of the gate axis; lane kq finishes window kq
-// of the group.  The steps run in the reverse of the forward's order.
+// (jp, k8) owns hidden units 2jp, 2jp+1 and the interleaved slice {32 i + 4 k8 + c} of the gate axis, so
+// each dgh value read from shared memory feeds two FMAs (the forward gets three per h value); a
+// reduce-scatter over the 8 slice lanes leaves every (window, unit) sum on the lane that finishes it.
+// The steps run in the reverse of the forward's order.
 //
 // Outputs:  dgi      [row][768]  n = d*384 + g*128 + j   (feeds dW_ih, db_ih, dX)
 //           dghn     [row][256]  the n-gate entry of dgh  (b_hh gradient)
@@ -28,21 +30,35 @@ rec_bwd_kernel(const float* __restrict__ dout, const float4* __restrict__ gates,
                float* __restrict__ dghn, float* __restrict__ dgh_prev, int nwin) {
     static_assert(NB == 1 || NB == 2 || NB == 4, "group size");
     __shared__ __align__(16) float ds[2][NB][DG_STRIDE];
-    const int tid = threadIdx.x, j = tid >> 2, kq = tid & 3;
+    // thread (jp, k8): hidden units 2jp and 2jp+1, gate-axis slice {32 i + 4 k8 + c}: every dgh value it reads
+    // from shared memory feeds two FMAs
+    const int tid = threadIdx.x, jp = tid >> 3, k8 = tid & 7;
     const int dir = blockIdx.x & 1;
     const float* whh = whh0 + dir * dir_stride;            // raw W_hh of this direction: [384][128]
 
-    float w[WHH_REGS];
+    float w0[48], w1[48];
 #pragma unroll
-    for (int i = 0; i < 24; ++i)
+    for (int i = 0; i < 12; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) w[i * 4 + c] = whh[(16 * i + 4 * kq + c) * HID + j];
+        for (int c = 0; c < 4; ++c) {
+            const float2 p = *reinterpret_cast<const float2*>(whh + (32 * i + 4 * k8 + c) * HID + 2 * jp);
+            w0[i * 4 + c] = p.x;
+            w1[i * 4 + c] = p.y;
+        }
+    // after the reduce-scatter over the 8 slice lanes, lane k8 = (b2 b1 b0) holds one (window, unit) sum:
+    //   NB = 4: window 2 b2 + b1, unit b0        NB = 2: window b2, unit b1 (b0 duplicates)
+    //   NB = 1: unit b2 (b1, b0 duplicate)
+    const int b2 = (k8 >> 2) & 1, b1 = (k8 >> 1) & 1, b0 = k8 & 1;
+    const int wb = NB == 4 ? 2 * b2 + b1 : NB == 2 ? b2 : 0;
+    const int o = NB == 4 ? b0 : NB == 2 ? b1 : b2;
+    const bool role = NB == 4 ? true : NB == 2 ? b0 == 0 : (k8 & 3) == 0;
+    const int j = 2 * jp + o;
 
     const int ngroups = (nwin + NB - 1) / NB;
     for (int grp = blockIdx.x >> 1; grp < ngroups; grp += gridDim.x >> 1) {
-        const int b0 = grp * NB;
-        const bool mine = kq < NB && (b0 + kq) < nwin;
-        const int row0 = (b0 + (mine ? kq : 0)) * COLS;
+        const int b0w = grp * NB;
+        const bool mine = role && (b0w + wb) < nwin;
+        const int row0 = (b0w + (mine ? wb : 0)) * COLS;
         // forward direction d ran t = 0..89 (d = 0) or 89..0 (d = 1); walk it backwards
         int t = dir ? 0 : COLS - 1;
         const int dt = dir ? 1 : -1;                         // t of the next step of THIS loop; h_prev sits at t + dt
@@ -85,7 +101,7 @@ rec_bwd_kernel(const float* __restrict__ dout, const float4* __restrict__ gates,
                     float* gp = dgh_prev + (row + dt) * GI_N + dir * G3 + j;
                     gp[0] = drp; gp[HID] = dzp; gp[2 * HID] = dq;
                 }
-                ds[nxt][kq][j] = drp; ds[nxt][kq][HID + j] = dzp; ds[nxt][kq][2 * HID + j] = dq;
+                ds[nxt][wb][j] = drp; ds[nxt][wb][HID + j] = dzp; ds[nxt][wb][2 * HID + j] = dq;
                 // a full step ahead: operands of the next loop step
                 if (s + 1 < COLS) {
                     const unsigned rn = row + dt;
@@ -95,37 +111,51 @@ rec_bwd_kernel(const float* __restrict__ dout, const float4* __restrict__ gates,
                 }
             }
             __syncthreads();
-            float acc[NB];
+            float v[NB][2];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+            for (int b = 0; b < NB; ++b) v[b][0] = v[b][1] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 24; ++i) {
+            for (int i = 0; i < 12; ++i) {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    const float4 dv = *reinterpret_cast<const float4*>(&ds[nxt][b][16 * i + 4 * kq]);
-                    acc[b] = fmaf(w[i * 4 + 0], dv.x, acc[b]);
-                    acc[b] = fmaf(w[i * 4 + 1], dv.y, acc[b]);
-                    acc[b] = fmaf(w[i * 4 + 2], dv.z, acc[b]);
-                    acc[b] = fmaf(w[i * 4 + 3], dv.w, acc[b]);
+                    const float4 dv = *reinterpret_cast<const float4*>(&ds[nxt][b][32 * i + 4 * k8]);
+                    v[b][0] = fmaf(w0[i * 4 + 0], dv.x, v[b][0]); v[b][1] = fmaf(w1[i * 4 + 0], dv.x, v[b][1]);
+                    v[b][0] = fmaf(w0[i * 4 + 1], dv.y, v[b][0]); v[b][1] = fmaf(w1[i * 4 + 1], dv.y, v[b][1]);
+                    v[b][0] = fmaf(w0[i * 4 + 2], dv.z, v[b][0]); v[b][1] = fmaf(w1[i * 4 + 2], dv.z, v[b][1]);
+                    v[b][0] = fmaf(w0[i * 4 + 3], dv.w, v[b][0]); v[b][1] = fmaf(w1[i * 4 + 3], dv.w, v[b][1]);
                 }
             }
+            // reduce-scatter over the 8 slice lanes (xor 4, 2, 1): each stage keeps the half this lane finishes
             float a;
             if (NB == 4) {
-                const bool hi1 = kq & 1, hi2 = kq & 2;
-                const float s0 = hi1 ? acc[0] : acc[1];
-                const float s1 = hi1 ? acc[2] : acc[3];
-                const float k0 = (hi1 ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, s0, 1);
-                const float k1 = (hi1 ? acc[3] : acc[2]) + __shfl_xor_sync(0xffffffffu, s1, 1);
-                const float sx = hi2 ? k0 : k1;
-                a = (hi2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, sx, 2);
-            } else {
+                float k1[2][2];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 1);
-                    acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 2);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int oo = 0; oo < 2; ++oo) {
+                        const float keep = b2 ? v[2 + h][oo] : v[h][oo], send = b2 ? v[h][oo] : v[2 + h][oo];
+                        k1[h][oo] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                float k2[2];
+#pragma unroll
+                for (int oo = 0; oo < 2; ++oo) {
+                    const float keep = b1 ? k1[1][oo] : k1[0][oo], send = b1 ? k1[0][oo] : k1[1][oo];
+                    k2[oo] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
                 }
-                a = acc[0];
-                if (NB == 2 && kq == 1) a = acc[NB - 1];
+                a = (b0 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);
+            } else if (NB == 2) {
+                float k1[2];
+#pragma unroll
+                for (int oo = 0; oo < 2; ++oo) {
+                    const float keep = b2 ? v[NB - 1][oo] : v[0][oo], send = b2 ? v[0][oo] : v[NB - 1][oo];
+                    k1[oo] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                a = (b1 ? k1[1] : k1[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k1[0] : k1[1], 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+            } else {
+                a = (b2 ? v[0][1] : v[0][0]) + __shfl_xor_sync(0xffffffffu, b2 ? v[0][0] : v[0][1], 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
             }
             carry = fmaf(dh, zz, a);
             t += dt;

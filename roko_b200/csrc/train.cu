@@ -94,6 +94,7 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
         const int row0 = tile * F2_ROWS;
         const int nrow = (rows50 - row0) < F2_ROWS ? (rows50 - row0) : F2_ROWS;
         __syncthreads();                                    // previous tile's readers are done
+#pragma unroll 5
         for (int i = tid; i < F2_ROWS * FC1; i += TR_THREADS)
             (&as[0][0])[i] = i < nrow * FC1 ? a1[(size_t)row0 * FC1 + i] : 0.f;
         for (int i = tid; i < F2_ROWS * 12; i += TR_THREADS) {
@@ -187,7 +188,8 @@ embed_grad_kernel(const float* __restrict__ dep, const uint8_t* __restrict__ x, 
         __syncthreads();
         const float* src = dep + (size_t)bp * PE;
         const uint32_t* bsrc = bits + (size_t)bp * MASK_WORDS;
-        for (int i = tid; i < PE; i += TR_THREADS) {
+#pragma unroll 8
+        for (int i = tid; i < PE; i += TR_THREADS) {        // 8 loads in flight per thread
             const int ee = i / READS;
             const bool keep = (bsrc[i >> 5] >> (i & 31)) & 1u;
             tile[ee][i - ee * READS] = keep ? src[i] * scale : 0.f;
@@ -296,7 +298,7 @@ cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const
                            int rows50, float scale, int num_sms, cudaStream_t s) {
     if (rows50 <= 0) return cudaSuccess;
     const int ntiles = (rows50 + F2_ROWS - 1) / F2_ROWS;
-    const int grid = ntiles < 2 * num_sms ? ntiles : 2 * num_sms;
+    const int grid = ntiles < 4 * num_sms ? ntiles : 4 * num_sms;
     fc2_bwd_kernel<<<grid, TR_THREADS, 0, s>>>(du, u, a1_dap, W2, dW2, db2, rows50, scale);
     return cudaGetLastError();
 }
@@ -325,7 +327,7 @@ cudaError_t launch_embed_grad(const float* dep, const uint8_t* x, const uint32_t
                               float scale, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
     const int nbp = nwin * COLS;
-    const int grid = nbp < 2 * num_sms ? nbp : 2 * num_sms;
+    const int grid = nbp < 4 * num_sms ? nbp : 4 * num_sms;         // 41 KB of shared memory each: 4 fit an SM
     embed_grad_kernel<<<grid, TR_THREADS, 0, s>>>(dep, x, bits, dE, nwin, scale);
     return cudaGetLastError();
 }

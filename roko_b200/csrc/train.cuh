@@ -63,7 +63,10 @@ cudaError_t launch_drop_mask(unsigned int site, size_t n, uint8_t* out, DropCfg 
 // ---- row-streaming front-end products on tcgen05 (train_tc.cu) -------------------------------------
 size_t train_tc_image_floats();
 cudaError_t train_tc_setup();
-cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s);
+cudaError_t launch_train_images(const float* raw, float* img, cudaStream_t s);
+cudaError_t launch_din_tc(int l, const float* dgi, const float* img, float* din, int rows, int num_sms, cudaStream_t s);
+cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
+                         int rows, int bn, int num_sms, cudaStream_t s);
 cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, float* a1, int rows, DropCfg d,
                           int num_sms, cudaStream_t s);
 cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s);

@@ -104,7 +104,7 @@ int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows,
     TCU(cudaMemsetAsync(w.u, 0, (size_t)rows * IN0P * sizeof(float), s));      // the 12 pad columns stay zero
     TCU(launch_embed_drop(x, raw + RAW_E, w.ep, w.bits, n_windows, d, m->status, s));
     if (m->train_tc) {   // a1 = dropout(relu(ep W1^T + b1))                     rnn_model.py:50-51
-        TCU(launch_train_images(raw + RAW_W1, m->train_img, s));
+        TCU(launch_train_images(raw, m->train_img, s));
         TCU(launch_fc1_tc(w.ep, m->train_img, raw + RAW_B1, w.a1, rows50, d, m->num_sms, s));
     } else {
         GemmArgs a{};
@@ -160,6 +160,12 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         TCU(launch_rec_bwd(w.dh, reinterpret_cast<const float4*>(w.gates[l]), w.out[l], raw + raw_whh(l, 0),
                            (size_t)raw_dir_size(l), dgi, w.dghn, w.dghp, n_windows, sms, s));
         for (int dir = 0; dir < 2; ++dir) {
+            if (m->train_tc >= 4) {                       // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
+                TCU(launch_tn_tc(dgi + dir * G3, GI_N, G3, in, in_ld, in_w, grad_raw + raw_wih(l, dir), in_w, rows, 256, sms, s));
+                TCU(launch_tn_tc(w.dghp + dir * G3, GI_N, G3, w.out[l] + dir * HID, OUT_W, HID, grad_raw + raw_whh(l, dir), HID,
+                                 rows, 128, sms, s));
+                continue;
+            }
             GemmArgs a{};                                 // dW_ih = dgi_d^T in
             a.A = dgi + dir * G3; a.lda = GI_N; a.B = in; a.ldb = in_ld; a.C = grad_raw + raw_wih(l, dir); a.ldc = in_w;
             a.M = G3; a.N = in_w; a.K = rows;
@@ -171,11 +177,15 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         }
         TCU(launch_gru_bias_grad(dgi, w.dghn, rows, grad_raw + raw_bih(l, 0), grad_raw + raw_bhh(l, 0),
                                  grad_raw + raw_bih(l, 1), grad_raw + raw_bhh(l, 1), s));
-        for (int dir = 0; dir < 2; ++dir) {               // d(in) = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd
-            GemmArgs a{};
-            a.A = dgi + dir * G3; a.lda = GI_N; a.B = m->raw_al + raw_al_off(raw_wih(l, dir)); a.ldb = in_w; a.C = w.din; a.ldc = in_ld;
-            a.M = rows; a.N = in_w; a.K = G3;
-            TCU(launch_gemm(a, true, false, dir == 0 ? EPI_STORE : EPI_ACC, 1, sms, s));
+        if (m->train_tc >= 3) {                           // d(in) = dgi W_ih, both directions in one K = 768 product
+            TCU(launch_din_tc(l, dgi, m->train_img, w.din, rows, sms, s));
+        } else {
+            for (int dir = 0; dir < 2; ++dir) {           // d(in) = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd
+                GemmArgs a{};
+                a.A = dgi + dir * G3; a.lda = GI_N; a.B = m->raw_al + raw_al_off(raw_wih(l, dir)); a.ldb = in_w; a.C = w.din; a.ldc = in_ld;
+                a.M = rows; a.N = in_w; a.K = G3;
+                TCU(launch_gemm(a, true, false, dir == 0 ? EPI_STORE : EPI_ACC, 1, sms, s));
+            }
         }
         if (l > 0)
             TCU(launch_drop_apply(w.din, w.dh, (size_t)rows * OUT_W, DROP_GRU0 + (l - 1), d, s));

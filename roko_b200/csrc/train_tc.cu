@@ -70,13 +70,15 @@ __device__ __forceinline__ float t_tf32_hi(float v) {
 
 enum { TEPI_STORE = 0, TEPI_FC1 = 1 };
 
-// C[m][0..NREAL) (row stride NREAL) = epilogue(A[m][0..KREAL) (row stride LDA) x W), W as KB pairs of
-// hi / lo images of BN rows x 32 floats; rows >= NREAL and columns >= KREAL of the images are zero.
-template <int BN, int KB, int LDA, int KREAL, int NREAL, int EPI>
+// C[m][0..NREAL) (row stride LDC) = epilogue(A[m][0..KREAL) (row stride LDA) x W), W as NT x KB pairs of
+// hi / lo images of BN rows x 32 floats ([n tile][k block][hi | lo]); image rows beyond NREAL and columns
+// beyond KREAL are zero.  Output tile t covers rows (t / NT) * 128.., columns (t % NT) * BN...
+template <int BN, int KB, int NT, int LDA, int KREAL, int NREAL, int LDC, int EPI>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const float* __restrict__ bias,
                  float* __restrict__ C, int M, int ntiles, DropCfg drop) {
-    static_assert(KREAL % 4 == 0 && NREAL % 4 == 0 && LDA % 4 == 0 && KB * T_BK >= KREAL && BN >= NREAL && 2 * BN <= 512, "shape");
+    static_assert(KREAL % 4 == 0 && NREAL % 4 == 0 && LDA % 4 == 0 && LDC % 4 == 0 && KB * T_BK >= KREAL && NT * BN >= NREAL
+                  && 2 * BN <= 512 && (EPI != 1 || NT == 1), "shape");
     constexpr int W_IMG = BN * T_BK * 4;
     constexpr int STAGE = t_stage_bytes(BN);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
@@ -115,7 +117,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         const int chunk = tid & 7, rr = tid >> 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = tile * T_BM;
+            const int m0 = (tile / NT) * T_BM;
             const float* arow[8];
             bool valid[8];
 #pragma unroll
@@ -161,11 +163,12 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const float* src = wimg + (size_t)(tile % NT) * KB * 2 * (W_IMG / 4);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it & 1;
                     t_mbar_wait(BAR(4 + s), ((it >> 1) & 1) ^ 1);
                     t_mbar_expect_tx(BAR(2 + s), 2 * W_IMG);
-                    t_bulk_g2s(sbase + s * STAGE + 2 * T_A_IMG, wimg + (size_t)kb * 2 * (W_IMG / 4), 2 * W_IMG, BAR(2 + s));
+                    t_bulk_g2s(sbase + s * STAGE + 2 * T_A_IMG, src + (size_t)kb * 2 * (W_IMG / 4), 2 * W_IMG, BAR(2 + s));
                 }
             }
         }
@@ -207,14 +210,14 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         int j = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1;
-            const int m0 = tile * T_BM;
+            const int m0 = (tile / NT) * T_BM, nbase = (tile % NT) * BN;
             t_mbar_wait(BAR(6 + buf), (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * BN;
             float* T = epi_stage + (warp - 6) * 32 * T_EPI_ROW;
             const int rsub = lane >> 3, csub = (lane & 7) * 4;      // read-back role: 4 rows x 8 float4 per instruction
 #pragma unroll 1
-            for (int c0 = 0; c0 < NREAL; c0 += 32) {
+            for (int c0 = 0; c0 < BN && nbase + c0 < NREAL; c0 += 32) {
                 uint32_t r[32];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -232,7 +235,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                         make_float4(__uint_as_float(r[qq * 4 + 0]), __uint_as_float(r[qq * 4 + 1]),
                                     __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
                 __syncwarp();
-                const int n = c0 + csub;                             // first of this lane's 4 columns
+                const int n = nbase + c0 + csub;                     // first of this lane's 4 columns
                 if (n < NREAL) {
                     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (EPI == TEPI_FC1) b = __ldg(reinterpret_cast<const float4*>(bias + n));
@@ -250,7 +253,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                             v.z = drop_keep(drop, DROP_FC1, e0 + 2) ? v.z * drop.scale : 0.f;
                             v.w = drop_keep(drop, DROP_FC1, e0 + 3) ? v.w * drop.scale : 0.f;
                         }
-                        if (m < M) *reinterpret_cast<float4*>(C + (size_t)m * NREAL + n) = v;
+                        if (m < M) *reinterpret_cast<float4*>(C + (size_t)m * LDC + n) = v;
                     }
                 }
                 __syncwarp();
@@ -267,34 +270,45 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
     }
 }
 
-// ---- dW1 = dap^T ep : a 100 x 200 output reduced over 576 000 rows --------------------------------------
-// Both operands are row-major with the REDUCTION index as the row, i.e. the transpose of what a K-major UMMA
-// operand wants.  Eight producer warps transpose 32-row blocks on the fly: lane = k (row inside the block), one
-// float4 of 4 output rows per task, written as 4 + 4 scalars (tf32 hi / lo) into the swizzled K-major images
-// -- for a fixed output row the 32 lanes fill exactly one 128-byte swizzle row, so the stores are conflict free.
-// Each CTA owns a contiguous range of row blocks, accumulates the whole 128 x 256 (100 x 200 used) tile in TMEM
-// and adds it to global memory once at the end.
+// ---- C += A^T B for row-major A [rows][lda], B [rows][ldb]: the weight-gradient products -----------------
+// (dW1 = dap^T ep over 576 000 rows; dW_ih = dgi^T in and dW_hh = dgh^T out over 11 520 rows per layer.)
+// Both operands have the REDUCTION index as the row, i.e. the transpose of what a K-major UMMA operand wants.
+// Eight producer warps transpose 32-row blocks on the fly: lane = k (row inside the block), one float4 of 4
+// output rows per task, written as 4 + 4 scalars (tf32 hi / lo) into the swizzled K-major images -- for a fixed
+// output row the 32 lanes fill exactly one 128-byte swizzle row, so the stores are conflict free.  A CTA owns
+// one 128 x BN output tile (blockIdx.y, blockIdx.z) and a contiguous range of row blocks (blockIdx.x of
+// gridDim.x splits), accumulates in TMEM and adds its tile to global memory once at the end.
+struct TnArgs {
+    const float* A; int lda; int Mreal;
+    const float* B; int ldb; int Nreal;
+    float* C; int ldc;
+    int rows;
+};
 constexpr int DW_THREADS = 288;                        // 8 producer warps (0-3 also epilogue) + 1 MMA warp
-constexpr int DW_BN = 256;
-constexpr int DW_STAGE = 2 * T_A_IMG + 2 * DW_BN * T_BK * 4;     // 96 KB
-constexpr int DW_SMEM = 2 * DW_STAGE + 1024 + 256;
-constexpr int DW_TASKS = FC1 / 4 + READS / 4;          // 25 quads of j + 50 quads of r
+__host__ __device__ constexpr int dw_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
+__host__ __device__ constexpr int dw_smem_bytes(int bn) { return 2 * dw_stage_bytes(bn) + 1024 + 256; }
+constexpr int DW_MAXT = 12;                            // tasks per producer warp: (128 + 256) / 4 quads over 8 warps
 
-__global__ void __launch_bounds__(DW_THREADS, 1)
-dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float* __restrict__ dW1, int rows) {
-    constexpr int W_IMG = DW_BN * T_BK * 4;
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DW_BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
+template <int BN>
+__global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
+    constexpr int W_IMG = BN * T_BK * 4;
+    constexpr int STAGE = dw_stage_bytes(BN);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
     extern __shared__ unsigned char t_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * DW_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const uint32_t sbase = t_smem_u32(smem);
     const uint32_t bar0 = t_smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };       // full[s] = s, empty[s] = 2+s, acc_full = 4
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    const int m0 = blockIdx.y * T_BM, n0 = blockIdx.z * BN;
+    const int ma = (g.Mreal - m0) < T_BM ? (g.Mreal - m0) : T_BM;        // rows / columns of this tile that exist
+    const int nb = (g.Nreal - n0) < BN ? (g.Nreal - n0) : BN;
+    const int qa = ma >> 2, ntasks = qa + (nb >> 2);
     // this CTA's range of 32-row blocks
-    const int nblocks = (rows + T_BK - 1) / T_BK;
+    const int nblocks = (g.rows + T_BK - 1) / T_BK;
     const int per = (nblocks + gridDim.x - 1) / gridDim.x;
     const int kb0 = blockIdx.x * per;
     const int kb1 = (kb0 + per) < nblocks ? (kb0 + per) : nblocks;
@@ -305,9 +319,9 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
         t_mbar_init(BAR(4), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // image rows the producers never write (j >= 100, r >= 200) feed accumulator rows / columns nobody reads:
+    // image rows the producers never write (beyond ma / nb) feed accumulator rows / columns nobody reads:
     // zero them once so they at least hold finite numbers
-    for (int i = tid; i < 2 * DW_STAGE / 16; i += DW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 2 * STAGE / 16; i += DW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem_u32(tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -323,30 +337,30 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
         for (int it = 0; it < nkb; ++it) {
             const int s = it & 1;
             const int row = (kb0 + it) * T_BK + lane;              // lane = k inside the block
-            const bool rv = row < rows;
-            float4 v[10];
+            const bool rv = row < g.rows;
+            float4 v[DW_MAXT];
 #pragma unroll
-            for (int i = 0; i < 10; ++i) {
+            for (int i = 0; i < DW_MAXT; ++i) {
                 const int t = warp + 8 * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < DW_TASKS && rv)
-                    v[i] = t < FC1 / 4 ? __ldg(reinterpret_cast<const float4*>(dap + (size_t)row * FC1 + 4 * t))
-                                       : __ldg(reinterpret_cast<const float4*>(ep + (size_t)row * READS + 4 * (t - FC1 / 4)));
+                if (t < ntasks && rv)
+                    v[i] = t < qa ? __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + m0 + 4 * t))
+                                  : __ldg(reinterpret_cast<const float4*>(g.B + (size_t)row * g.ldb + n0 + 4 * (t - qa)));
             }
             t_mbar_wait(BAR(2 + s), ((it >> 1) & 1) ^ 1);
-            unsigned char* st = smem + s * DW_STAGE;
+            unsigned char* st = smem + s * STAGE;
 #pragma unroll
-            for (int i = 0; i < 10; ++i) {
+            for (int i = 0; i < DW_MAXT; ++i) {
                 const int t = warp + 8 * i;
-                if (t < DW_TASKS) {
-                    const bool isA = t < FC1 / 4;
+                if (t < ntasks) {
+                    const bool isA = t < qa;
                     unsigned char* hi = st + (isA ? 0 : 2 * T_A_IMG);
                     unsigned char* lo = hi + (isA ? T_A_IMG : W_IMG);
-                    const int n0 = 4 * (isA ? t : t - FC1 / 4);
+                    const int r0 = 4 * (isA ? t : t - qa);
                     const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int n = n0 + c;
+                        const int n = r0 + c;
                         const int off = (n >> 3) * 1024 + (n & 7) * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4;
                         const float h = t_tf32_hi(e[c]);
                         *reinterpret_cast<float*>(hi + off) = h;
@@ -364,7 +378,7 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
             const int s = it & 1;
             t_mbar_wait(BAR(s), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = sbase + s * DW_STAGE, a_lo = a_hi + T_A_IMG;
+            const uint32_t a_hi = sbase + s * STAGE, a_lo = a_hi + T_A_IMG;
             const uint32_t w_hi = a_lo + T_A_IMG, w_lo = w_hi + W_IMG;
 #pragma unroll
             for (int kk = 0; kk < T_BK / 8; ++kk) {
@@ -384,10 +398,11 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
         // ------------------------------- epilogue: TMEM -> global adds ------------------------------
         t_mbar_wait(BAR(4), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int j = warp * 32 + lane;                              // TMEM lane == output row
+        const int j = warp * 32 + lane;                              // TMEM lane == row inside the tile
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        float* crow = g.C + (size_t)(m0 + j) * g.ldc + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < READS; c0 += 32) {
+        for (int c0 = 0; c0 < nb; c0 += 32) {
             uint32_t r[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -399,10 +414,10 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (j < FC1) {
+            if (j < ma) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (c0 + i < READS) atomicAdd(dW1 + j * READS + c0 + i, __uint_as_float(r[i]));
+                    if (c0 + i < nb) atomicAdd(crow + c0 + i, __uint_as_float(r[i]));
             }
         }
     }
@@ -414,12 +429,28 @@ dw1_tc_kernel(const float* __restrict__ dap, const float* __restrict__ ep, float
     }
 }
 
-cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s) {
-    if (rows <= 0) return cudaSuccess;
+// C[Mreal][Nreal] (row stride ldc, zeroed or holding earlier partial sums) += A^T B.  Mreal, Nreal, lda, ldb
+// multiples of 4, A and B 16-byte aligned.  bn = 128 or 256: the tile width.
+cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
+                         int rows, int bn, int num_sms, cudaStream_t s) {
+    if (rows <= 0 || Mreal <= 0 || Nreal <= 0) return cudaSuccess;
+    if ((lda | ldb | Mreal | Nreal) & 3) return cudaErrorInvalidValue;
+    const int mt = (Mreal + T_BM - 1) / T_BM, nt = (Nreal + bn - 1) / bn;
     const int nblocks = (rows + T_BK - 1) / T_BK;
-    const int grid = nblocks < num_sms ? nblocks : num_sms;
-    dw1_tc_kernel<<<grid, DW_THREADS, DW_SMEM, s>>>(dap, ep, dW1, rows);
+    int splits = num_sms / (mt * nt);                    // about one CTA per SM ...
+    const int maxs = (nblocks + 7) / 8;                  // ... but at least 8 row blocks each: a tile's epilogue is up to 32 K atomics
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+    TnArgs g{A, lda, Mreal, B, ldb, Nreal, C, ldc, rows};
+    dim3 grid(splits, mt, nt);
+    if (bn == 256) tn_tc_kernel<256><<<grid, DW_THREADS, dw_smem_bytes(256), s>>>(g);
+    else if (bn == 128) tn_tc_kernel<128><<<grid, DW_THREADS, dw_smem_bytes(128), s>>>(g);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
+}
+
+cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s) {
+    return launch_tn_tc(dap, FC1, FC1, ep, READS, READS, dW1, READS, rows, 256, num_sms, s);
 }
 
 // ---- weight images -------------------------------------------------------------------------------------
@@ -450,21 +481,85 @@ __global__ void train_images_kernel(const float* __restrict__ W1, float* __restr
     img[p] = half == 0 ? hi : v - hi;
 }
 
-size_t train_tc_image_floats() { return (size_t)IMG_FC1_FLOATS + IMG_DEP_FLOATS; }
+// d(in) = dgi W_ih over both directions: rows n = input feature (tiles of 256), k = gate column of dgi
+// (d*384 + g*128 + j, 24 blocks of 32):  W_ih[d][g*128 + j][n]
+constexpr int DIN_BN = 256, DIN_KB = GI_N / T_BK;
+__host__ __device__ constexpr int din_ntiles(int l) { return (gru_in(l) + DIN_BN - 1) / DIN_BN; }
+__host__ __device__ constexpr int din_img_floats(int l) { return din_ntiles(l) * DIN_KB * 2 * DIN_BN * T_BK; }
+__host__ __device__ constexpr int din_img_off(int l) {
+    int off = IMG_FC1_FLOATS + IMG_DEP_FLOATS;
+    for (int i = 0; i < l; ++i) off += din_img_floats(i);
+    return off;
+}
+constexpr int IMG_TOTAL_FLOATS = din_img_off(LAYERS);
 
-cudaError_t train_tc_setup() {
-    cudaError_t e = cudaFuncSetAttribute(tc_stream_kernel<FC1_BN, FC1_KB, READS, READS, FC1, TEPI_FC1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(FC1_BN));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(dw1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+__global__ void din_images_kernel(const float* __restrict__ raw, float* __restrict__ img) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x + din_img_off(0);
+    if (p >= IMG_TOTAL_FLOATS) return;
+    int l = 0;
+    while (l + 1 < LAYERS && p >= din_img_off(l + 1)) ++l;
+    const int kin = gru_in(l);
+    constexpr int img_floats = DIN_BN * T_BK;
+    int i = p - din_img_off(l);
+    const int ntile = i / (DIN_KB * 2 * img_floats);
+    i %= DIN_KB * 2 * img_floats;
+    const int kb = i / (2 * img_floats);
+    i %= 2 * img_floats;
+    const int half = i / img_floats;
+    const int ob = (i % img_floats) * 4;
+    const int rgrp = ob / 1024, within = ob % 1024;
+    const int r8 = within / 128, pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+    const int n = ntile * DIN_BN + rgrp * 8 + r8;
+    const int k = kb * T_BK + ((pchunk ^ r8) * 4) + w4;              // undo the 128-byte swizzle
+    const int d = k / G3, q = k - d * G3;
+    const float v = n < kin ? raw[raw_wih(l, d) + q * kin + n] : 0.f;
+    const float hi = t_tf32_hi(v);
+    img[p] = half == 0 ? hi : v - hi;
 }
 
-cudaError_t launch_train_images(const float* W1, float* img, cudaStream_t s) {
+size_t train_tc_image_floats() { return (size_t)IMG_TOTAL_FLOATS; }
+
+cudaError_t train_tc_setup() {
+    cudaError_t e = cudaFuncSetAttribute(tc_stream_kernel<FC1_BN, FC1_KB, 1, READS, READS, FC1, FC1, TEPI_FC1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(FC1_BN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_STORE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(256));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(128));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_stream_kernel<DIN_BN, DIN_KB, 2, GI_N, GI_N, IN0, IN0P, TEPI_STORE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DIN_BN));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_stream_kernel<DIN_BN, DIN_KB, 1, GI_N, GI_N, OUT_W, OUT_W, TEPI_STORE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DIN_BN));
+}
+
+// raw: the model's flat fp32 weights (state_dict order)
+cudaError_t launch_train_images(const float* raw, float* img, cudaStream_t s) {
     const int n = IMG_FC1_FLOATS + IMG_DEP_FLOATS;
-    train_images_kernel<<<(n + 255) / 256, 256, 0, s>>>(W1, img);
+    train_images_kernel<<<(n + 255) / 256, 256, 0, s>>>(raw + RAW_W1, img);
+    const int nd = IMG_TOTAL_FLOATS - din_img_off(0);
+    din_images_kernel<<<(nd + 255) / 256, 256, 0, s>>>(raw, img);
+    return cudaGetLastError();
+}
+
+// d(in) of GRU layer l = dgi [rows][768] x W_ih (both directions) -> din [rows][gru_inp(l)]
+cudaError_t launch_din_tc(int l, const float* dgi, const float* img, float* din, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    DropCfg none{0ull, 0u, 1.f};
+    const int mt = (rows + T_BM - 1) / T_BM;
+    if (l == 0) {
+        const int ntiles = mt * 2, grid = ntiles < num_sms ? ntiles : num_sms;
+        tc_stream_kernel<DIN_BN, DIN_KB, 2, GI_N, GI_N, IN0, IN0P, TEPI_STORE>
+            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(0), nullptr, din, rows, ntiles, none);
+    } else {
+        const int grid = mt < num_sms ? mt : num_sms;
+        tc_stream_kernel<DIN_BN, DIN_KB, 1, GI_N, GI_N, OUT_W, OUT_W, TEPI_STORE>
+            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(l), nullptr, din, rows, mt, none);
+    }
     return cudaGetLastError();
 }
 
@@ -474,7 +569,7 @@ cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, fl
     if (rows <= 0) return cudaSuccess;
     const int ntiles = (rows + T_BM - 1) / T_BM;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
-    tc_stream_kernel<FC1_BN, FC1_KB, READS, READS, FC1, TEPI_FC1>
+    tc_stream_kernel<FC1_BN, FC1_KB, 1, READS, READS, FC1, FC1, TEPI_FC1>
         <<<grid, T_THREADS, t_smem_bytes(FC1_BN), s>>>(ep, img, b1, a1, rows, ntiles, d);
     return cudaGetLastError();
 }
@@ -485,7 +580,7 @@ cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int ro
     const int ntiles = (rows + T_BM - 1) / T_BM;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     DropCfg none{0ull, 0u, 1.f};
-    tc_stream_kernel<DEP_BN, DEP_KB, FC1, FC1, READS, TEPI_STORE>
+    tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_STORE>
         <<<grid, T_THREADS, t_smem_bytes(DEP_BN), s>>>(dap, img + IMG_FC1_FLOATS, nullptr, dep, rows, ntiles, none);
     return cudaGetLastError();
 }

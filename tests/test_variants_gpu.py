@@ -55,14 +55,14 @@ for k, p in m.named_parameters():
     flat = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
     ref = g["sample/" + k].astype(np.float64)
     err = np.abs(flat[TO.sample_index(flat.size)] - ref).max() / (np.abs(ref).max() + 1e-30)
-    assert err <= 5e-5, (k, err)
+    assert err <= 1e-4, (k, err)
 print("OK")
 """ % (ROOT, os.path.join(ROOT, "tests", "golden", "train_seed1.npz"), os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"))
 
 
 @pytest.mark.parametrize("env", [
     {"ROKO_B200_REC_NB": "2"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_PROJ": "ffma"},
-    {"ROKO_B200_TRAIN_TC": "1"}, {"ROKO_B200_TRAIN_TC": "0"}, {"ROKO_B200_TRAIN_TC": "0", "ROKO_B200_GEMM_NOSTREAM": "1"},
+    {"ROKO_B200_TRAIN_TC": "3"}, {"ROKO_B200_TRAIN_TC": "2"}, {"ROKO_B200_TRAIN_TC": "1"}, {"ROKO_B200_TRAIN_TC": "0"}, {"ROKO_B200_TRAIN_TC": "0", "ROKO_B200_GEMM_NOSTREAM": "1"},
 ], ids=lambda e: ",".join(f"{k.replace('ROKO_B200_', '')}={v}" for k, v in e.items()))
 def test_training_kernel_variant(env):
     """The recurrence's window-group sizes (forward with saved gates, and backward) and the projection

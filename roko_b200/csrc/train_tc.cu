@@ -17,7 +17,8 @@ constexpr int T_A_IMG = T_BM * T_BK * 4;               // 16 KB
 constexpr int T_EPI_ROW = 36;
 constexpr int T_EPI_BYTES = 4 * 32 * T_EPI_ROW * 4;
 __host__ __device__ constexpr int t_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
-__host__ __device__ constexpr int t_smem_bytes(int bn) { return 2 * t_stage_bytes(bn) + 1024 + 256 + T_EPI_BYTES; }
+__host__ __device__ constexpr int t_stages(int bn) { return bn <= 128 ? 3 : 2; }     // what fits 227 KB
+__host__ __device__ constexpr int t_smem_bytes(int bn) { return t_stages(bn) * t_stage_bytes(bn) + 1024 + 256 + T_EPI_BYTES; }
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t_mbar_init(uint32_t bar, uint32_t count) {
@@ -81,25 +82,29 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                   && 2 * BN <= 512 && (EPI != 1 || NT == 1), "shape");
     constexpr int W_IMG = BN * T_BK * 4;
     constexpr int STAGE = t_stage_bytes(BN);
+    constexpr int NS = t_stages(BN);                       // operand pipeline depth
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
     extern __shared__ unsigned char t_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    float* epi_stage = reinterpret_cast<float*>(smem + 2 * STAGE + 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* epi_stage = reinterpret_cast<float*>(smem + NS * STAGE + 256);
     const uint32_t sbase = t_smem_u32(smem);
     const uint32_t bar0 = t_smem_u32(bars);
-    // barriers: full_a[s] = s, full_w[s] = 2+s, empty[s] = 4+s, acc_full[b] = 6+b, acc_empty[b] = 8+b
+    // barriers: full_a[s] = s, full_w[s] = NS+s, empty[s] = 2NS+s, acc_full[b] = 3NS+b, acc_empty[b] = 3NS+2+b
     auto BAR = [&](int i) { return bar0 + 8u * i; };
+    constexpr int B_FW = NS, B_EM = 2 * NS, B_AF = 3 * NS, B_AE = 3 * NS + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
             t_mbar_init(BAR(s), 128);
-            t_mbar_init(BAR(2 + s), 1);
-            t_mbar_init(BAR(4 + s), 1);
-            t_mbar_init(BAR(6 + s), 1);
-            t_mbar_init(BAR(8 + s), 128);
+            t_mbar_init(BAR(B_FW + s), 1);
+            t_mbar_init(BAR(B_EM + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            t_mbar_init(BAR(B_AF + b), 1);
+            t_mbar_init(BAR(B_AE + b), 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -114,6 +119,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
 
     if (warp < 4) {
         // ------------------------------- A producers ----------------------------------------------
+        // two k blocks of loads in flight per thread (registers), NS blocks in shared memory
         const int chunk = tid & 7, rr = tid >> 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -126,13 +132,17 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                 valid[i] = (m0 + r) < M;
                 arow[i] = A + (size_t)(valid[i] ? m0 + r : 0) * LDA + chunk * 4;
             }
-            float4 v[8];
+            float4 v[2][8];
+            auto load_block = [&](float4 (&dst)[8], int kb) {
+                const bool kin = kb * T_BK + chunk * 4 < KREAL;             // the last k block may be partly padding
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                v[i] = (valid[i] && chunk * 4 < KREAL) ? __ldg(reinterpret_cast<const float4*>(arow[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it & 1;
-                t_mbar_wait(BAR(4 + s), ((it >> 1) & 1) ^ 1);
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = (valid[i] && kin) ? __ldg(reinterpret_cast<const float4*>(arow[i] + kb * T_BK))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            auto store_block = [&](const float4 (&src)[8]) {
+                const int s = it % NS;
+                t_mbar_wait(BAR(B_EM + s), ((it / NS) & 1) ^ 1);
                 unsigned char* ahi = smem + s * STAGE;
                 unsigned char* alo = ahi + T_A_IMG;
 #pragma unroll
@@ -140,21 +150,26 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                     const int r = rr + 16 * i;
                     const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
                     float4 h, l;
-                    h.x = t_tf32_hi(v[i].x); l.x = v[i].x - h.x;
-                    h.y = t_tf32_hi(v[i].y); l.y = v[i].y - h.y;
-                    h.z = t_tf32_hi(v[i].z); l.z = v[i].z - h.z;
-                    h.w = t_tf32_hi(v[i].w); l.w = v[i].w - h.w;
+                    h.x = t_tf32_hi(src[i].x); l.x = src[i].x - h.x;
+                    h.y = t_tf32_hi(src[i].y); l.y = src[i].y - h.y;
+                    h.z = t_tf32_hi(src[i].z); l.z = src[i].z - h.z;
+                    h.w = t_tf32_hi(src[i].w); l.w = src[i].w - h.w;
                     *reinterpret_cast<float4*>(ahi + off) = h;
                     *reinterpret_cast<float4*>(alo + off) = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 t_mbar_arrive(BAR(s));
+                ++it;
+            };
+            load_block(v[0], 0);
+            if (KB > 1) load_block(v[1], 1);
+#pragma unroll 1
+            for (int kb = 0; kb < KB; kb += 2) {
+                store_block(v[0]);
+                if (kb + 2 < KB) load_block(v[0], kb + 2);
                 if (kb + 1 < KB) {
-                    const bool kin = (kb + 1) * T_BK + chunk * 4 < KREAL;      // the last k block may be partly padding
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[i] = (valid[i] && kin) ? __ldg(reinterpret_cast<const float4*>(arow[i] + (kb + 1) * T_BK))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                    store_block(v[1]);
+                    if (kb + 3 < KB) load_block(v[1], kb + 3);
                 }
             }
         }
@@ -165,10 +180,10 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const float* src = wimg + (size_t)(tile % NT) * KB * 2 * (W_IMG / 4);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it & 1;
-                    t_mbar_wait(BAR(4 + s), ((it >> 1) & 1) ^ 1);
-                    t_mbar_expect_tx(BAR(2 + s), 2 * W_IMG);
-                    t_bulk_g2s(sbase + s * STAGE + 2 * T_A_IMG, src + (size_t)kb * 2 * (W_IMG / 4), 2 * W_IMG, BAR(2 + s));
+                    const int s = it % NS;
+                    t_mbar_wait(BAR(B_EM + s), ((it / NS) & 1) ^ 1);
+                    t_mbar_expect_tx(BAR(B_FW + s), 2 * W_IMG);
+                    t_bulk_g2s(sbase + s * STAGE + 2 * T_A_IMG, src + (size_t)kb * 2 * (W_IMG / 4), 2 * W_IMG, BAR(B_FW + s));
                 }
             }
         }
@@ -179,14 +194,14 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         int it = 0, j = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1;
-            t_mbar_wait(BAR(8 + buf), ((j >> 1) & 1) ^ 1);
+            t_mbar_wait(BAR(B_AE + buf), ((j >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = buf * BN;
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
+                const int s = it % NS;
+                const uint32_t ph = (it / NS) & 1;
                 t_mbar_wait(BAR(s), ph);
-                t_mbar_wait(BAR(2 + s), ph);
+                t_mbar_wait(BAR(B_FW + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = sbase + s * STAGE, a_lo = a_hi + T_A_IMG;
                 const uint32_t w_hi = a_lo + T_A_IMG, w_lo = w_hi + W_IMG;
@@ -198,10 +213,10 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                     t_umma_tf32(d, dah, dwl, IDESC, 1u, elected);
                     t_umma_tf32(d, dah, dwh, IDESC, 1u, elected);
                 }
-                if (elected) t_umma_commit(BAR(4 + s));
+                if (elected) t_umma_commit(BAR(B_EM + s));
                 __syncwarp();
             }
-            if (elected) t_umma_commit(BAR(6 + buf));
+            if (elected) t_umma_commit(BAR(B_AF + buf));
             __syncwarp();
         }
     } else {
@@ -211,7 +226,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
             const uint32_t buf = j & 1;
             const int m0 = (tile / NT) * T_BM, nbase = (tile % NT) * BN;
-            t_mbar_wait(BAR(6 + buf), (j >> 1) & 1);
+            t_mbar_wait(BAR(B_AF + buf), (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * BN;
             float* T = epi_stage + (warp - 6) * 32 * T_EPI_ROW;
@@ -259,7 +274,7 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
                 __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            t_mbar_arrive(BAR(8 + buf));
+            t_mbar_arrive(BAR(B_AE + buf));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

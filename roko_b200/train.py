@@ -116,6 +116,50 @@ class InMemoryTrainDataset(Dataset):
         return len(self.X)
 
 
+class SlabLoader:
+    """Batches of an ``InMemoryTrainDataset`` without the per-item path of ``DataLoader``: one gather per batch
+    (``index_select`` into two reusable staging buffers, pinned when the target is a CUDA device) instead of 128
+    ``__getitem__`` calls and a collate, then an asynchronous copy to ``device``.  Same semantics as
+    ``DataLoader(ds, batch_size, shuffle)``: a fresh permutation per epoch from ``generator``, the ragged last
+    batch kept.  A staging buffer is rewritten only after the copy that last read it has completed (one CUDA
+    event per buffer), so the host may run ahead of the device by a step without corrupting a batch."""
+
+    def __init__(self, ds, batch_size, shuffle=False, generator=None, device="cpu"):
+        self.x = torch.from_numpy(np.ascontiguousarray(ds.X))
+        self.y = torch.from_numpy(np.ascontiguousarray(ds.Y))
+        self.batch_size, self.shuffle, self.generator = int(batch_size), shuffle, generator
+        self.device = torch.device(device)
+        self.n = self.x.shape[0]
+        pin = self.device.type == "cuda"
+        self.bufs = [(torch.empty((self.batch_size,) + tuple(self.x.shape[1:]), dtype=self.x.dtype, pin_memory=pin),
+                      torch.empty((self.batch_size,) + tuple(self.y.shape[1:]), dtype=self.y.dtype, pin_memory=pin))
+                     for _ in range(2)]
+        self.copied = [None, None]
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        order = torch.randperm(self.n, generator=self.generator) if self.shuffle else torch.arange(self.n)
+        for k, lo in enumerate(range(0, self.n, self.batch_size)):
+            idx = order[lo:lo + self.batch_size]
+            slot = k & 1
+            bx, by = self.bufs[slot]
+            m = idx.numel()
+            if self.copied[slot] is not None:
+                self.copied[slot].synchronize()                 # the device has finished reading this buffer
+            torch.index_select(self.x, 0, idx, out=bx[:m])
+            torch.index_select(self.y, 0, idx, out=by[:m])
+            if self.device.type != "cuda":
+                yield bx[:m].clone(), by[:m].clone()
+                continue
+            dx = bx[:m].to(self.device, non_blocking=True)
+            dy = by[:m].to(self.device, non_blocking=True)
+            self.copied[slot] = torch.cuda.Event()
+            self.copied[slot].record(torch.cuda.current_stream(self.device))
+            yield dx, dy
+
+
 class EarlyStopping:
     """ignite.handlers.EarlyStopping(patience, score_function, trainer) with min_delta 0."""
 
@@ -198,12 +242,18 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
     gen = torch.Generator()
     gen.manual_seed(shuffle_seed)
     pin = torch.cuda.is_available()
-    train_dl = DataLoader(train_ds, batch_size, shuffle=True, num_workers=workers, pin_memory=pin, generator=gen)
-    val_dl = DataLoader(val_ds, batch_size, num_workers=workers, pin_memory=pin) if val_ds is not None else None
+    if mem:                                                                 # batch-granular gathers, no per-item collate
+        train_dl = val_dl = None                                            # built once the device is known
+    else:
+        train_dl = DataLoader(train_ds, batch_size, shuffle=True, num_workers=workers, pin_memory=pin, generator=gen)
+        val_dl = DataLoader(val_ds, batch_size, num_workers=workers, pin_memory=pin) if val_ds is not None else None
 
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     device = torch.device(device)
+    if mem:
+        train_dl = SlabLoader(train_ds, batch_size, shuffle=True, generator=gen, device=device)
+        val_dl = SlabLoader(val_ds, batch_size, device=device) if val_ds is not None else None
     if model is None:
         model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)          # raises without a B200: no CPU path
     if world > 1:
@@ -214,7 +264,7 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
         + (f"  val windows: {len(val_ds)}" if val_ds is not None else ""))
 
     history = {"train_loss": [], "val_acc": [], "val_loss": [], "checkpoint": None, "epochs": 0}
-    running = None
+    running = None                       # ignite's RunningAverage, kept on the device: no host sync per step
     for epoch in range(1, epochs + 1):
         for i, (x, y) in enumerate(train_dl, 1):
             if world > 1:                                                   # this rank's slice of the batch
@@ -231,11 +281,11 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
                 rdist.average_gradients(model)
             optim.step()
             if loss is not None:
-                v = loss.item()
-                running = v if running is None else running * RUNNING_ALPHA + (1.0 - RUNNING_ALPHA) * v
+                v = loss.detach()
+                running = v.clone() if running is None else running.mul_(RUNNING_ALPHA).add_(v, alpha=1.0 - RUNNING_ALPHA)
             if i % 100 == 0:
-                log(f"ITERATION {i}/{len(train_dl)} - loss: {running}")
-        history["train_loss"].append(running)
+                log(f"ITERATION {i}/{len(train_dl)} - loss: {float(running) if running is not None else None}")
+        history["train_loss"].append(float(running) if running is not None else None)
         history["epochs"] = epoch
         if val_dl is None:
             continue

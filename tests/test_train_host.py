@@ -102,3 +102,25 @@ def test_cli_signature_matches_reference():
     with pytest.raises(SystemExit):
         T.main(["--help"])
     assert (T.BATCH_SIZE, T.EPOCHS, T.LR, T.PATIENCE) == (128, 100, 1e-4, 7)
+
+
+def test_slab_loader_matches_dataset_rows_and_shuffles():
+    x, y = _register("mem://train_e", 21, seed=12)
+    ds = T.InMemoryTrainDataset("mem://train_e", transform=T.TrainToTensor(), h5=fake_h5)
+    seq = T.SlabLoader(ds, 8)
+    assert len(seq) == 3
+    got = list(seq)
+    assert [b[0].shape[0] for b in got] == [8, 8, 5]                    # the ragged last batch is kept
+    assert np.array_equal(torch.cat([b[0] for b in got]).numpy(), x) and np.array_equal(torch.cat([b[1] for b in got]).numpy(), y)
+    assert got[0][0].dtype == torch.uint8 and got[0][1].dtype == torch.int64
+    g = torch.Generator().manual_seed(3)
+    sh = T.SlabLoader(ds, 8, shuffle=True, generator=g)
+    a = torch.cat([b[1] for b in sh]).numpy()
+    b = torch.cat([b[1] for b in sh]).numpy()                            # a new permutation every epoch
+    assert not np.array_equal(a, y) and not np.array_equal(a, b)
+    y64 = y.astype(np.int64)
+    assert sorted(map(bytes, a)) == sorted(map(bytes, y64)) == sorted(map(bytes, b))   # each epoch is a permutation of the rows
+    pairs = {bytes(xx): bytes(yy) for xx, yy in zip(x, y64)}
+    for bx, by in T.SlabLoader(ds, 8, shuffle=True, generator=g):        # rows stay paired with their labels
+        for xx, yy in zip(bx.numpy(), by.numpy()):
+            assert pairs[bytes(xx)] == bytes(yy)

@@ -157,6 +157,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = cudaMalloc(&m->raw_al, (size_t)(RAW_TOTAL + RAW_AL_PAD) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&m->train_img, train_tc_image_floats() * sizeof(float));
     if (e == cudaSuccess) e = train_tc_setup();
+    if (e == cudaSuccess) e = gemm_setup();
     if (const char* tt = getenv("ROKO_B200_TRAIN_TC")) m->train_tc = atoi(tt);
     if (e == cudaSuccess) e = cudaMalloc(&m->status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));

@@ -305,16 +305,34 @@ __global__ void __launch_bounds__(G_THREADS, 2) sgemm_stream_kernel(const GemmAr
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <bool KA, bool KB, int EPI>
+constexpr int stream_smem_bytes() { return F_STAGES * (f_tile_floats<KA>() + f_tile_floats<KB>()) * (int)sizeof(float); }
+
+template <bool KA, bool KB, int EPI>
 static cudaError_t launch_stream(const GemmArgs& g, dim3 grid, cudaStream_t s) {
-    constexpr int bytes = F_STAGES * (f_tile_floats<KA>() + f_tile_floats<KB>()) * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sgemm_stream_kernel<KA, KB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    sgemm_stream_kernel<KA, KB, EPI><<<grid, G_THREADS, bytes, s>>>(g);
+    sgemm_stream_kernel<KA, KB, EPI><<<grid, G_THREADS, stream_smem_bytes<KA, KB, EPI>(), s>>>(g);
     return cudaGetLastError();
+}
+
+template <bool KA, bool KB>
+static cudaError_t setup_kab() {
+    cudaError_t e = cudaFuncSetAttribute(sgemm_stream_kernel<KA, KB, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         stream_smem_bytes<KA, KB, EPI_STORE>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgemm_stream_kernel<KA, KB, EPI_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   stream_smem_bytes<KA, KB, EPI_ACC>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgemm_stream_kernel<KA, KB, EPI_ATOMIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   stream_smem_bytes<KA, KB, EPI_ATOMIC>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sgemm_stream_kernel<KA, KB, EPI_FC1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   stream_smem_bytes<KA, KB, EPI_FC1>());
+    return e;
+}
+
+// opt the streamed kernels into > 48 KB of dynamic shared memory on the CURRENT device (called per model_create)
+cudaError_t gemm_setup() {
+    cudaError_t e = setup_kab<true, true>();
+    if (e == cudaSuccess) e = setup_kab<true, false>();
+    if (e == cudaSuccess) e = setup_kab<false, true>();
+    if (e == cudaSuccess) e = setup_kab<false, false>();
+    return e;
 }
 
 template <bool KA, bool KB>

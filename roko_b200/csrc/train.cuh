@@ -43,6 +43,7 @@ struct GemmArgs {
     bool vecA, vecB;         // filled by the launcher
 };
 cudaError_t launch_gemm(GemmArgs g, bool ka, bool kb, int epi, int splits, int num_sms, cudaStream_t s);
+cudaError_t gemm_setup();
 
 // ---- element-wise / small kernels (train.cu) -----------------------------------------------------
 constexpr int MASK_WORDS = 320;          // keep bits of one (window, column)'s 10 000 embedding outputs (313 words used)

@@ -32,9 +32,6 @@ if ROOT not in sys.path:
 READS, COLS, CLASSES = 200, 90, 5
 WIN_BYTES = READS * COLS
 STAGES = ["front", "proj0", "rec0", "proj1", "rec1", "proj2", "rec2", "head"]
-KERNEL_OF = {"front": "front_kernel", "proj0": "proj_tc3_kernel<512>", "proj1": "proj_tc3_kernel<256>",
-             "proj2": "proj_tc3_kernel<256>", "rec0": "rec_kernel", "rec1": "rec_kernel", "rec2": "rec_kernel",
-             "head": "head_kernel"}
 # algorithmic FLOPs per window (fc1 one-hot factorised)
 FLOPS = {"front": 90 * (200 * 100 + 2 * 100 * 50 * 12) + 2 * 90 * 50 * 100 * 10,
          "proj0": 2 * 90 * 768 * 500, "proj1": 2 * 90 * 768 * 256, "proj2": 2 * 90 * 768 * 256,
@@ -174,10 +171,10 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    batch, steps, warm = args.batch, args.steps, max(1, min(args.warmup, 3))
+    batch, steps, warm = args.batch, args.steps, max(1, args.warmup)
     ref = CpuReference()
     per_win = ref.probe()
-    # each step is a bounded sample of the batch so that K steps end within ~2 minutes
+    # each step is a bounded sample of the batch so that W + K steps end within ~2 minutes
     budget = 120.0
     sample = int(max(1, min(batch, budget / (steps + warm) / per_win)))
     ref.timed(warm, sample)
@@ -199,6 +196,76 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class StockTorchGpu:
+    """Baseline B: the reference's operator sequence on the SAME B200 through stock torch --
+    embedding gather, permute + cuBLAS fc1/fc2, the cuDNN multi-layer bidirectional GRU, fc4, argmax
+    (roko/rnn_model.py:46-59 after ``.to('cuda')``, roko/inference.py:91-116).  Library kernels only;
+    none of this repo's kernels are on this path."""
+
+    def __init__(self, state_dict, dev):
+        import torch
+        self.torch, self.dev = torch, dev
+        self.sd = {k: v.detach().to(dev, torch.float32) for k, v in state_dict.items()}
+        self.gru = torch.nn.GRU(500, 128, num_layers=3, batch_first=True, bidirectional=True).to(dev)
+        own = self.gru.state_dict()
+        for k in own:
+            own[k].copy_(self.sd["gru." + k])
+        self.gru.eval()
+        self.gru.flatten_parameters()
+
+    def predict(self, x_u8):
+        torch, F, sd = self.torch, self.torch.nn.functional, self.sd
+        x = x_u8.long()                                                       # inference.py:113
+        h = F.embedding(x, sd["embedding.weight"]).permute((0, 2, 3, 1))      # rnn_model.py:47-48
+        h = F.relu(F.linear(h, sd["fc1.weight"], sd["fc1.bias"]))             # :50
+        h = F.relu(F.linear(h, sd["fc2.weight"], sd["fc2.bias"]))             # :53
+        h, _ = self.gru(h.reshape(-1, 90, 500))                               # :56-57
+        return torch.argmax(F.linear(h, sd["fc4.weight"], sd["fc4.bias"]), dim=2)   # :59, inference.py:116
+
+    def windows_per_s(self, pool, batch, min_s=0.4):
+        """Device-timed steady-state throughput at `batch` windows per call over a pool of resident inputs."""
+        torch = self.torch
+        xs = pool.view(-1, READS, COLS)
+        n = xs.shape[0] // batch
+        with torch.no_grad():
+            for i in range(3):
+                self.predict(xs[(i % n) * batch:(i % n + 1) * batch])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            done, ms = 0, 0.0
+            while ms < min_s * 1e3 and done < 2000:
+                e0.record()
+                for i in range(8):
+                    self.predict(xs[((done + i) % n) * batch:((done + i) % n + 1) * batch])
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+                done += 8
+        return done * batch / (ms * 1e-3)
+
+
+def run_torch_gpu(args):
+    """bench.py --impl torch_gpu: baseline B as its own JSON line (same metric / config as the default arm)."""
+    import torch
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"), map_location="cpu")
+    g = torch.Generator(device=dev).manual_seed(1234)
+    pool = torch.randint(0, 12, (args.pool_batches, args.batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)
+    stock = StockTorchGpu(sd, dev)
+    wps = stock.windows_per_s(pool, args.batch)
+    print(json.dumps({
+        "impl": "torch_gpu", "metric": "consensus_windows_per_sec", "value": wps, "unit": "windows/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": 3, "ms_per_step": args.batch / wps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1] geometry through STOCK torch on the GPU (cuBLAS + cuDNN GRU), batch={args.batch}",
+                   "batch": args.batch, "tf32": bool(torch.backends.cuda.matmul.allow_tf32), "torch": torch.__version__},
+        "gpu_launches": 0}), flush=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -206,6 +273,7 @@ def run_ours(args):
     from roko_b200 import _cabi
     from roko_b200 import dist as rdist
     from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+    from roko_b200.synth import structured_windows
 
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
@@ -218,54 +286,86 @@ def run_ours(args):
     peaks = load_peaks()
 
     # ---- model: rank 0 loads the .pth, NCCL-broadcasts the weights ---------------------------------
+    sd = torch.load(os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"), map_location="cpu")
     model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
     if rank == 0:
-        model.load_state_dict(torch.load(os.path.join(ROOT, "tests", "golden", "rand_seed1.pth"), map_location="cpu"))
-    model = model.to(dev).eval()
+        model.load_state_dict(sd)
+    model = model.to(dev).eval().requires_grad_(False)
     bcast_bytes = rdist.broadcast_weights(model, src=0) if world > 1 else 0
-    # throughput configuration: several batches in flight on different streams, tensor-core recurrence
-    # from 128 windows on (it occupies 8 SMs per batch instead of 128, at a higher per-batch latency)
+    # throughput configuration: several batches in flight on different streams; the tensor-core recurrence
+    # occupies 8 SMs per 128-window batch, so batches on other streams run beside it
     model.set_option("rec_tc_min", args.rec_tc_min)
+    for name in ("proj", "rec", "front", "graphs"):
+        v = getattr(args, name)
+        if v is not None:
+            model.set_option(name, v)
 
-    # ---- parity gate before any timing: golden vectors must come out bit-exact ---------------------
-    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_seed1.npz"))
+    # ---- parity gate before any timing, on the SAME kernels the timed loop runs: one full 128-window batch
+    # (the reference class's own logits / labels, tests/golden/golden_b128_seed1.npz) through the same call ------
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_b128_seed1.npz"))
+    gx = structured_windows(128, seed=int(gold["seed"]))
+    assert int(gx.astype(np.int64).sum()) == int(gold["x_crc"]), "synthetic generator drifted from the fixture"
     with torch.no_grad():
-        lab, logit = model.predict(torch.from_numpy(gold["x"]).to(dev), return_logits=True)
+        lab, logit = model.predict(torch.from_numpy(gx).to(dev), return_logits=True)
     perr = float(np.abs(logit.cpu().numpy() - gold["logits"]).max())
     if perr > 1e-4 or not np.array_equal(lab.cpu().numpy(), gold["labels"]):
         raise SystemExit(f"parity gate failed on rank {rank}: max logit err {perr}")
+    model.check_codes()
 
     # ---- synthetic pool, larger than L2 so no step re-reads its input from cache -------------------
     P = args.pool_batches
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = torch.randint(0, 12, (P, batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)
+
+    def make_pool(r):
+        g = torch.Generator(device=dev).manual_seed(1234 + r)
+        return torch.randint(0, 12, (P, batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)
+
+    pool = make_pool(rank)
     labels_all = torch.empty((K, batch, COLS), dtype=torch.uint8, device=dev)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     main = torch.cuda.current_stream(dev)
 
-    def run_steps(n, out):
+    def run_steps(n, out, src=None, first=0):
+        src = pool if src is None else src
         for s in streams:
             s.wait_stream(main)
         for i in range(n):
             with torch.cuda.stream(streams[i % NS]):
-                model.predict(pool[i % P], out=out[i % out.shape[0]])
+                model.predict(src[(first + i) % P], out=out[i % out.shape[0]])
         for s in streams:
             main.wait_stream(s)
+
+    def block(first):
+        """K steps (one per 128-window batch, NS batches in flight) + this block's label gather when N > 1."""
+        run_steps(K, labels_all, first=first)
+        return rdist.gather_labels(labels_all.view(K * batch, COLS), K * batch * world) if world > 1 else None
 
     with torch.no_grad():
         run_steps(W, labels_all)
         torch.cuda.synchronize()
+        # calibration: how many K-step blocks make a timed region of >= min_region seconds
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(main)
+        block(0)
+        c1.record(main)
+        torch.cuda.synchronize()
+        R = max(1, min(args.max_blocks, int(np.ceil(args.min_region * 1e3 / max(c0.elapsed_time(c1), 1e-3)))))
+        if world > 1:
+            t = torch.tensor([R], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            R = int(t.item())
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+            time.sleep(0.12)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw0 = time.perf_counter()
         e0.record(main)
-        run_steps(K, labels_all)
-        gathered = rdist.gather_labels(labels_all.view(K * batch, COLS), K * batch * world) if world > 1 else None
+        gathered = None
+        for r in range(R):                               # R blocks of exactly K steps, back to back (no sync between)
+            gathered = block(r * K)
         e1.record(main)
         torch.cuda.synchronize()
         tw1 = time.perf_counter()
@@ -276,14 +376,30 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        if rank == 0:
-            assert gathered is not None and gathered.shape == (K * batch * world, COLS)
-    value = K * batch * world / (ms * 1e-3)
+    value = R * K * batch * world / (ms * 1e-3)
+
+    # ---- N > 1: what rank 0 gathered over NVLink must equal, byte for byte, what ONE GPU computes for every
+    # rank's inputs (rank 0 regenerates each rank's seeded pool and replays that rank's last block) -----------
+    shard_check = None
+    if world > 1 and rank == 0:
+        assert gathered is not None and gathered.shape == (K * batch * world, COLS)
+        ok = True
+        with torch.no_grad():
+            for r in range(world):
+                src = pool if r == 0 else make_pool(r)
+                mine = torch.empty((K, batch, COLS), dtype=torch.uint8, device=dev)
+                run_steps(K, mine, src=src, first=(R - 1) * K)
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(mine.view(K * batch, COLS), gathered[r * K * batch:(r + 1) * K * batch]))
+                del src
+        if not ok:
+            raise SystemExit("multi-GPU check failed: gathered labels differ from the single-GPU labels")
+        shard_check = "gathered labels of every rank == single-GPU recomputation, byte for byte"
 
     # ---- e2e: pinned host windows -> labels on the host, through the public API ---------------------
-    # all K steps' inputs sit in pinned host memory (K*batch windows, cycling the device pool's contents);
-    # ONE predict_host call moves them to the device, runs the path and brings the labels back.
-    Kh = min(K, max(1, (512 << 20) // (batch * WIN_BYTES)))             # pinned staging capped at 512 MB
+    # K steps' inputs sit in pinned host memory; ONE predict_host call moves them to the device, runs the
+    # path and brings the labels back.  Calls repeat until the region is >= min_region seconds.
+    Kh = min(max(K, 160), max(1, (768 << 20) // (batch * WIN_BYTES)))   # >= 160 batches per call (9 device passes), <= 768 MB pinned
     x_host = torch.empty((Kh * batch, READS, COLS), dtype=torch.uint8).pin_memory()
     for i0 in range(0, Kh, P):
         n = min(P, Kh - i0)
@@ -294,18 +410,25 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    done = 0
-    while done < K:                                                     # one call unless K exceeds the staging cap
-        n = min(Kh, K - done)
-        model.predict_host(x_host[:n * batch], batch=batch, out=y_host[:n * batch])
-        done += n
+    calls = 0
+    while True:
+        model.predict_host(x_host, batch=batch, out=y_host)
+        calls += 1
+        e2e_s = time.perf_counter() - t0
+        stop = e2e_s >= args.min_region or calls >= 64
+        if world > 1:                                                   # every rank makes the same number of calls
+            t = torch.tensor([1.0 if stop else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            stop = bool(t.item() > 0)
+        if stop:
+            break
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = K * batch * world / e2e_s
-    # clocks sampled inside the two timed regions (device-resident steps, end-to-end call)
+    e2e_value = calls * Kh * batch * world / e2e_s
+    # clocks sampled inside the two timed regions (device-resident steps, end-to-end calls)
     clocks = sampler.stop([(tw0, tw1), (t0, t0 + e2e_s)]) if rank == 0 else None
     del x_host
 
@@ -317,29 +440,26 @@ def run_ours(args):
     _cabi.check(lib.roko_b200_forward_timed(h.ptr, pool[0].data_ptr(), batch, labels_all[0].data_ptr(), ws.data_ptr(),
                                              ws.numel(), main.cuda_stream, 20, st))
     stage_ms = dict(zip(STAGES, [float(v) for v in st]))
-    step_rec = "rec_tc_kernel" if (args.rec_tc_min and batch >= max(args.rec_tc_min, 64)) else "rec_kernel"
+    names = kernel_names(args, batch)
     kern_ms = {}
     for sname, v in stage_ms.items():
-        kern_ms.setdefault(step_rec if sname.startswith("rec") else KERNEL_OF[sname], []).append((sname, v))
+        kern_ms.setdefault(names[sname], []).append((sname, v))
     dom_kernel = max(kern_ms, key=lambda k: sum(v for _, v in kern_ms[k]))
     dom_stage = max(kern_ms[dom_kernel], key=lambda sv: sv[1])[0]
     dom_launch_ms = statistics.mean(v for _, v in kern_ms[dom_kernel])
     dom_flops = statistics.mean(FLOPS[s] for s, _ in kern_ms[dom_kernel]) * batch
     achieved_tf = dom_flops / (dom_launch_ms * 1e-3) / 1e12
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    dom_ctas = {"rec_tc_kernel": 2 * ((batch + 31) // 32), "rec_kernel": min(2 * ((batch + 1) // 2), sms),
-                "front_kernel": min(batch, sms), "head_kernel": sms}.get(dom_kernel, sms)
+    dom_ctas = {"rec_h_kernel": 2 * ((batch + 31) // 32), "rec_tc_kernel": 2 * ((batch + 31) // 32),
+                "rec_kernel": min(2 * ((batch + 1) // 2), sms), "front_kernel": min(batch, sms),
+                "front_tc_kernel": min(batch, sms), "head_kernel": sms}.get(dom_kernel, sms)
     fp32 = ctypes.c_double()
     _cabi.check(lib.roko_b200_measure_fp32_peak(local_rank, ctypes.byref(fp32)))
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        # ncu names carry template arguments (rec_kernel<2>, proj_tc_kernel<512, 1>): match on the stem
-        stem = dom_kernel.split("<")[0]
-        cands = [v for k, v in tj.items() if k.split("<")[0].split("@")[0] == stem and k.endswith(f"@B{batch}")
-                 and (("<" not in dom_kernel) or dom_kernel.split("<")[1].split(">")[0].split(",")[0] in k)]
-        traffic = (sum(cands) / len(cands)) if cands else None
+        traffic = tj.get(f"{dom_kernel}@B{batch}")
     except Exception:
         pass
 
@@ -354,11 +474,10 @@ def run_ours(args):
                                              ws_big.numel(), main.cuda_stream, 10, st2))
     big_ms = dict(zip(STAGES, [float(v) for v in st2]))
     big_total = sum(big_ms.values())
-    rec_name = "rec_tc_kernel" if (args.rec_tc_min and big >= max(args.rec_tc_min, 64)) else "rec_kernel"
+    big_names = kernel_names(args, big)
     big_kernels = {}
     for sname, v in big_ms.items():
-        kname = KERNEL_OF[sname] if not sname.startswith("rec") else rec_name
-        d = big_kernels.setdefault(kname, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        d = big_kernels.setdefault(big_names[sname], {"ms": 0.0, "flops": 0.0, "launches": 0})
         d["ms"] += v; d["flops"] += FLOPS[sname] * big; d["launches"] += 1
     for d in big_kernels.values():
         d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
@@ -367,37 +486,61 @@ def run_ours(args):
         del d["flops"]
     del ws_big
 
+    # ---- baseline B: the stock torch operator sequence (cuBLAS + cuDNN GRU) on this same GPU ----------
+    vs_library = None
+    if rank == 0 and not args.no_library_baseline:
+        try:
+            stock = StockTorchGpu(sd, dev)
+            lib128 = stock.windows_per_s(pool, batch)
+            lib1024 = stock.windows_per_s(pool, 1024)
+            vs_library = {"torch_gpu_windows_per_s": lib128, "torch_gpu_windows_per_s_b1024": lib1024,
+                          "ratio": value / world / lib128, "ratio_vs_b1024": value / world / lib1024,
+                          "note": "reference operator sequence through stock torch on this GPU (cuBLAS fp32 + cuDNN GRU), "
+                                  "device-resident inputs, per-GPU; tf32=%s" % bool(torch.backends.cuda.matmul.allow_tf32)}
+            del stock
+        except Exception as ex:                                          # a library failure must not cost the bench line
+            vs_library = {"unavailable": repr(ex)[:200]}
+
     if world > 1:
         dist.barrier()
     if rank == 0:
         line = {
             "metric": "consensus_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": ms / (R * K), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "blocks": R, "timed_region_s": ms * 1e-3,
             "config": {
                 "workload": f"BASELINE configs[1]: batch={batch} synthetic windows (200 reads x 90 cols, uint8 codes 0..11) "
                             "per step on each GPU, random-init weights tests/golden/rand_seed1.pth, labels out (uint8)",
                 "batch": batch, "windows_per_step_all_gpus": batch * world, "parallelism": f"dp{world}",
-                "streams": NS, "e2e_note": "predict_host coalesces consecutive batches into device passes of <= 2368 windows "
-                                           "(windows are independent), so e2e exceeds the per-call batch-128 device number",
+                "streams": NS,
+                "timing": f"{R} blocks of exactly {K} steps back to back between one CUDA-event pair (blocks repeat until the "
+                          f"region is >= {args.min_region} s so that a short --steps run is steady state); ms_per_step = region / ({R} x {K})",
+                "e2e_note": "predict_host coalesces consecutive batches into device passes of <= 2368 windows "
+                            "(windows are independent), so e2e can exceed the per-call batch-128 device number",
                 "l2": f"inputs cycle through a {P * batch * WIN_BYTES / 1e6:.0f} MB pool (> 126 MB L2)",
-                "collectives": "ncclBroadcast weights %d B before timing; label all-gather inside the timed region" % bcast_bytes
+                "collectives": ("ncclBroadcast weights %d B before timing; label all-gather of every block inside the timed region" % bcast_bytes)
                                if world > 1 else "none (1 GPU)",
+                "kernels": names,
             },
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": batch * WIN_BYTES,
-                    "d2h_bytes_per_step": batch * COLS, "api": "RNN.predict_host -> roko_b200_infer_host (pinned host buffers)"},
-            "gpu_launches": K * 8,
+                    "d2h_bytes_per_step": batch * COLS, "api": "RNN.predict_host -> roko_b200_infer_host (pinned host buffers)",
+                    "calls": calls, "windows_per_call": Kh * batch, "timed_region_s": e2e_s},
+            "gpu_launches": R * K * 8,
             "clocks": clocks,
-            "parity": {"golden_max_abs_logit_err": perr, "golden_labels_exact": True},
+            "parity": {"batch128_max_abs_logit_err": perr, "batch128_labels_exact": True,
+                       "fixture": "tests/golden/golden_b128_seed1.npz (reference class outputs), same kernels as the timed loop",
+                       "multi_gpu": shard_check},
             "roofline": {"bound": "tensor", "kernel": dom_kernel, "stage": dom_stage, "achieved": achieved_tf,
                          "ctas_per_launch": dom_ctas, "sms": sms,
                          "frac_on_occupied_sms": achieved_tf / (peaks["bf16_tflops_sustained"] * min(dom_ctas, sms) / sms),
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": traffic,
                          "peak_source": peaks["source"] + " bf16 dense, sustained (kernel timed inside the step)",
-                         "note": "per-launch figure of one 128-window batch; in this throughput configuration a launch of the tensor-core "
-                                 "recurrence occupies only ctas_per_launch SMs while other batches run beside it; the "
-                                 "whole-chip picture is coalesced.kernels"},
+                         "note": "per-launch figure of one 128-window batch; algorithmic fp32 FLOPs (the tensor kernels spend 3 "
+                                 "fp16 MMAs per product, so the MMA rate is 3x this); a launch of the tensor-core recurrence "
+                                 "occupies only ctas_per_launch SMs while other batches run beside it; the whole-chip picture is "
+                                 "coalesced.kernels"},
             "fp32": {"peak_tflops_measured": fp32.value, "kernel_frac": achieved_tf / fp32.value if fp32.value else None,
                      "path_tflops": value / world * FLOPS_PER_WINDOW / 1e12,
                      "path_frac": value / world * FLOPS_PER_WINDOW / 1e12 / fp32.value if fp32.value else None},
@@ -407,10 +550,13 @@ def run_ours(args):
             "stage_ms": stage_ms,
             "coalesced": {"windows_per_pass": big, "windows_per_s_per_gpu": big / (big_total * 1e-3), "ms_per_pass": big_total,
                           "stage_ms": big_ms, "kernels": big_kernels,
+                          "path_tflops": big / (big_total * 1e-3) * FLOPS_PER_WINDOW / 1e12,
+                          "path_frac_of_bf16_tensor_peak": big / (big_total * 1e-3) * FLOPS_PER_WINDOW / 1e12 / peaks["bf16_tflops_sustained"],
                           "note": "device-resident, one stream, consecutive steps fused into one pass (what predict_host does); "
-                                  "TFLOP/s are algorithmic fp32 FLOPs: the tensor kernels spend 3 tf32 MMAs per product"},
+                                  "TFLOP/s are algorithmic fp32 FLOPs: the tensor kernels spend 3 fp16 MMAs per product"},
+            "vs_library": vs_library,
         }
-        if world == 1:
+        if world == 1 and not args.no_train:
             tms, _ = train_steps(dev, 128, 20, 3)
             line["training"] = {"windows_per_s": 128 / (tms * 1e-3), "ms_per_step": tms, "batch": 128,
                                 "note": "roko train.py step (train-mode forward with dropout, cross-entropy, hand-written "
@@ -423,6 +569,17 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_names(args, nwin):
+    """Which kernel runs each stage of the chain for a chunk of `nwin` windows under this run's options."""
+    proj = {None: "proj_h_kernel", 4: "proj_h_kernel", 3: "proj_tc3_kernel", 0: "proj_kernel"}[args.proj]
+    rec_tc = {None: "rec_h_kernel", 2: "rec_h_kernel", 1: "rec_tc_kernel"}[args.rec]
+    if not (args.rec_tc_min and nwin >= args.rec_tc_min) or (rec_tc == "rec_tc_kernel" and nwin < 64):
+        rec_tc = "rec_kernel"
+    front = "front_tc_kernel" if args.front == 1 else "front_kernel"
+    return {"front": front, "proj0": proj + "<512>", "proj1": proj + "<256>", "proj2": proj + "<256>",
+            "rec0": rec_tc, "rec1": rec_tc, "rec2": rec_tc, "head": "head_kernel"}
 
 
 def train_steps(dev, batch, steps, warmup, world=1, seed=0):
@@ -503,16 +660,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--streams", type=int, default=8)
-    ap.add_argument("--rec-tc-min", type=int, default=128, help="windows from which the recurrence runs on tcgen05")
+    ap.add_argument("--rec-tc-min", type=int, default=64, help="windows from which the recurrence runs on tcgen05")
+    ap.add_argument("--proj", type=int, default=None, help="projection kernel: 4 fp16 tcgen05 (default), 3 tf32 tcgen05, 0 FFMA")
+    ap.add_argument("--rec", type=int, default=None, help="tensor-core recurrence: 2 fp16 (default), 1 tf32")
+    ap.add_argument("--front", type=int, default=None, help="front end: 0 mma.sync stages, 1 tcgen05 stages (library default if unset)")
+    ap.add_argument("--graphs", type=int, default=None, help="CUDA-graph replay of the chain: 1 on (default), 0 off")
+    ap.add_argument("--min-region", type=float, default=0.5, help="repeat the K-step block until the timed region is this long (s)")
+    ap.add_argument("--max-blocks", type=int, default=2000)
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--pool-batches", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--coalesce", type=int, default=2368, help="windows in the coalesced device pass (extra fields)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     elif args.mode == "train":
         run_train(args)
     else:

@@ -30,6 +30,7 @@ extern "C" {
 #define ROKO_B200_ECUDA 2    /* a CUDA runtime call failed; message carries cudaGetErrorString */
 #define ROKO_B200_ESTATE 3   /* model has no weights loaded */
 #define ROKO_B200_ECODES 4   /* an input code was outside 0..11 (nn.Embedding would raise IndexError) */
+#define ROKO_B200_ERANGE 5   /* a weight or activation left the range of the fp16-split tensor-core kernels */
 
 typedef struct roko_b200_model roko_b200_model;
 

@@ -10,6 +10,9 @@ runs it on seeded structured pileups on the CPU in eval mode and stores
   golden_seed1.npz        x (16,200,90) u8, logits (16,90,5) f32, labels (16,90) u8 (argmax as
                           inference.py:116), stage taps for the first 2 windows
                           (front (2,90,500), gru_l0..2 (2,90,256))
+  golden_b128_seed1.npz   one full inference batch: x = structured_windows(128, seed=501) (not stored: regenerated
+                          from the seed), logits (128,90,5) f32, labels (128,90) u8 -- the batch of BASELINE.json
+                          configs[1]; bench.py's parity gate and the tensor-core-recurrence tests run on it
   edge_seed1.npz          edge-case windows (all one code, all UNKNOWN, codes 0 and 11 only,
                           single strand) with logits/labels
 
@@ -74,6 +77,12 @@ def main():
                         **{f"tap_{k}": v for k, v in taps.items()})
     print("golden: label hist", np.bincount(labels.ravel(), minlength=5),
           "min top-2 gap", float(np.min(np.sort(logits, 2)[..., -1] - np.sort(logits, 2)[..., -2])))
+
+    xb = structured_windows(128, seed=501)
+    lb, yb, _ = run_ref(model, xb)
+    np.savez_compressed(os.path.join(OUT, "golden_b128_seed1.npz"), seed=np.int64(501), logits=lb, labels=yb,
+                        x_crc=np.int64(int(np.frombuffer(xb.tobytes(), dtype=np.uint8).astype(np.int64).sum())))
+    print("b128: label hist", np.bincount(yb.ravel(), minlength=5))
 
     edge = np.zeros((6, 200, 90), dtype=np.uint8)
     edge[0][:] = 0                                 # all 'A' forward

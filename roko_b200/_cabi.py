@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libroko_b200.so")
 
-OK, EARG, ECUDA, ESTATE, ECODES = 0, 1, 2, 3, 4
+OK, EARG, ECUDA, ESTATE, ECODES, ERANGE = 0, 1, 2, 3, 4, 5
 
 c_model_p = ctypes.c_void_p
 

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libroko_b200.so")
 OBJ = os.path.join(CSRC, "build")
-SOURCES = ["pack.cu", "front.cu", "proj.cu", "proj_tc.cu", "proj_tc2.cu", "proj_tc3.cu", "rec.cu", "rec_tc.cu", "head.cu", "api.cu",
+SOURCES = ["pack.cu", "front.cu", "proj.cu", "proj_tc3.cu", "proj_h.cu", "rec.cu", "rec_tc.cu", "rec_h.cu", "head.cu", "api.cu",
            "gemm.cu", "train.cu", "train_tc.cu", "rec_bwd.cu", "train_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -68,7 +68,7 @@ def build(verbose=False, force=False):
                 sys.stderr.write(log)
     if _stale(LIB, objs):
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
-               "-o", LIB] + objs
+               "-o", LIB] + objs + ["-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")

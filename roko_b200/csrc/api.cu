@@ -4,7 +4,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
+#include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/roko_b200.h"
 #include "model.h"
@@ -30,6 +34,12 @@ int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
 constexpr size_t WIN_BYTES = (size_t)READS * COLS;                  // 18 000
 constexpr size_t WS_WIN_BYTES = WS_PER_WINDOW * sizeof(float) + WIN_BYTES;
 
+// NVTX range around a C-ABI call (visible in nsys / ncu --nvtx; a no-op without an attached tool)
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -53,20 +63,20 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
                 cudaEvent_t* ev = nullptr) {
     const long long cap_ll = (long long)(ws_bytes / per_window_bytes);
     if (cap_ll < 1) return fail(ROKO_B200_EARG, "workspace smaller than one window%s%s");
-    const int cap = cap_ll > n ? n : (int)cap_ll;
+    int cap = cap_ll > n ? n : (int)cap_ll;
+    if (cap > 16384) cap = 16384;               // keeps the kernels' 32-bit element offsets in range
     if (taps && cap < n) return fail(ROKO_B200_EARG, "forward_taps needs the whole batch in the workspace%s%s");
     float* u = static_cast<float*>(ws);
     float* gi = u + (size_t)cap * WS_U;
     float* h0 = gi + (size_t)cap * WS_GI;
     float* h1 = h0 + (size_t)cap * WS_H;
     const float* pk = m->packed;
-    const size_t dstride = (size_t)(pk_whh(0, 1) - pk_whh(0, 0));
 
     for (int c0 = 0; c0 < n; c0 += cap) {
         const int nc = (n - c0) < cap ? (n - c0) : cap;
         const int rows = nc * COLS;
         if (ev) CU(cudaEventRecord(ev[0], s));
-        CU(launch_front(m->fc, x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
+        CU(launch_front(x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
         if (taps && taps->front)
             CU(cudaMemcpy2DAsync(taps->front, IN0 * sizeof(float), u, IN0P * sizeof(float), IN0 * sizeof(float),
                                  rows, cudaMemcpyDeviceToDevice, s));
@@ -76,12 +86,7 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
             if (ev) CU(cudaEventRecord(ev[1 + 2 * l], s));
             CU(proj_dispatch(m, in, l, gi, rows, s));
             if (ev) CU(cudaEventRecord(ev[2 + 2 * l], s));
-            // (>= 64 windows also keeps rec_tc's unguarded gi reads of a ragged last group inside the scratch)
-            if (m->rec_tc_min > 0 && nc >= m->rec_tc_min && nc >= 64)
-                CU(launch_rec_tc(gi, pk + pk_rtc(l, 0), pk + pk_rtc(l, 0) + RTC_W, (size_t)RTC_DIR,
-                                 pk + pk_rtc(l, 0) + 2 * RTC_W, outs[l], nc, m->num_sms, s));
-            else
-                CU(launch_rec(gi, pk + pk_whh(l, 0), dstride, pk + pk_bhn(l, 0), outs[l], nc, m->num_sms, s));
+            CU(rec_dispatch(m, gi, l, outs[l], nc, s));
             if (taps && taps->gru[l])
                 CU(cudaMemcpyAsync(taps->gru[l], outs[l], (size_t)rows * OUT_W * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
@@ -92,6 +97,91 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
                        labels ? labels + (size_t)c0 * COLS : nullptr, rows, s));
         if (ev) CU(cudaEventRecord(ev[8], s));
     }
+    return ROKO_B200_OK;
+}
+
+// ---- CUDA-graph replay of the 8-kernel chain ------------------------------------------------------
+// A forward over a batch that fits the workspace is always the same 8 launches; only the input and
+// output pointers differ from call to call.  The chain is captured once per (batch size, workspace,
+// outputs wanted) and replayed with cudaGraphLaunch after patching the first kernel's `x` and the last
+// kernel's `logits` / `labels` (cudaGraphExecKernelNodeSetParams): one driver call instead of eight, and
+// no host-side gaps between the kernels of a batch.  A graph instance runs one launch at a time, so
+// callers that keep several batches in flight use one workspace (hence one instance) per stream.
+constexpr int GRAPH_UNAVAILABLE = -1;
+constexpr size_t MAX_GRAPHS = 64;
+
+void drop_graphs(roko_b200_model* m) {
+    for (auto* e : m->graphs) {
+        if (e->exec) cudaGraphExecDestroy(e->exec);
+        if (e->graph) cudaGraphDestroy(e->graph);
+        delete e;
+    }
+    m->graphs.clear();
+}
+
+int graph_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint8_t* labels, void* ws, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(m->mu);
+    roko_b200_model::GraphEntry* e = nullptr;
+    for (auto* c : m->graphs)
+        if (c->n == n && c->ws == ws && c->want_logits == (logits != nullptr) && c->want_labels == (labels != nullptr)) { e = c; break; }
+    if (!e) {
+        if (m->graphs.size() >= MAX_GRAPHS) {                       // evict the least recently used instance
+            size_t lru = 0;
+            for (size_t i = 1; i < m->graphs.size(); ++i) if (m->graphs[i]->last_use < m->graphs[lru]->last_use) lru = i;
+            auto* old = m->graphs[lru];
+            cudaGraphExecDestroy(old->exec); cudaGraphDestroy(old->graph); delete old;
+            m->graphs.erase(m->graphs.begin() + lru);
+        }
+        e = new (std::nothrow) roko_b200_model::GraphEntry();
+        if (!e) return GRAPH_UNAVAILABLE;
+        e->n = n; e->ws = ws; e->want_logits = logits != nullptr; e->want_labels = labels != nullptr;
+        bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int rc = run_forward(m, x, n, logits, labels, ws, (size_t)n * WS_PER_WINDOW * sizeof(float), s, nullptr,
+                                       WS_PER_WINDOW * sizeof(float));
+            const cudaError_t ce = cudaStreamEndCapture(s, &e->graph);
+            ok = rc == ROKO_B200_OK && ce == cudaSuccess && e->graph;
+        }
+        if (ok) ok = cudaGraphInstantiate(&e->exec, e->graph, 0) == cudaSuccess;
+        if (ok) {   // the chain is linear: its root is the front-end kernel, its leaf the head kernel
+            size_t nn = 0;
+            ok = cudaGraphGetNodes(e->graph, nullptr, &nn) == cudaSuccess && nn >= 2 && nn <= 16;
+            cudaGraphNode_t nodes[16];
+            if (ok) ok = cudaGraphGetNodes(e->graph, nodes, &nn) == cudaSuccess;
+            for (size_t i = 0; ok && i < nn; ++i) {
+                size_t ndep = 0, nout = 0;
+                cudaGraphNodeType ty;
+                ok = cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
+                     cudaGraphNodeGetDependencies(nodes[i], nullptr, &ndep) == cudaSuccess &&
+                     cudaGraphNodeGetDependentNodes(nodes[i], nullptr, &nout) == cudaSuccess;
+                if (ok && ndep == 0) e->front = nodes[i];
+                if (ok && nout == 0) e->head = nodes[i];
+            }
+            ok = ok && e->front && e->head && e->front != e->head &&
+                 cudaGraphKernelNodeGetParams(e->front, &e->fp) == cudaSuccess &&
+                 cudaGraphKernelNodeGetParams(e->head, &e->hp) == cudaSuccess;
+            if (ok) {   // front_kernel(x, packed, u, nwin, status); head_kernel(h, w4, b4, logits, labels, rows)
+                for (int i = 0; i < 5; ++i) e->fargs[i] = e->fp.kernelParams[i];
+                for (int i = 0; i < 6; ++i) e->hargs[i] = e->hp.kernelParams[i];
+                e->fargs[0] = &e->x; e->hargs[3] = &e->logits; e->hargs[4] = &e->labels;
+                e->fp.kernelParams = e->fargs; e->hp.kernelParams = e->hargs;
+            }
+        }
+        if (!ok) {
+            cudaGetLastError();                                     // clear the sticky capture error, fall back for good
+            if (e->exec) cudaGraphExecDestroy(e->exec);
+            if (e->graph) cudaGraphDestroy(e->graph);
+            delete e;
+            m->use_graphs = 0;
+            return GRAPH_UNAVAILABLE;
+        }
+        m->graphs.push_back(e);
+    }
+    e->last_use = ++m->graph_clock;
+    e->x = x; e->logits = logits; e->labels = labels;
+    CU(cudaGraphExecKernelNodeSetParams(e->exec, e->front, &e->fp));
+    CU(cudaGraphExecKernelNodeSetParams(e->exec, e->head, &e->hp));
+    CU(cudaGraphLaunch(e->exec, s));
     return ROKO_B200_OK;
 }
 
@@ -163,19 +253,15 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
     if (e == cudaSuccess) e = front_setup();
     if (e == cudaSuccess) e = rec_setup();
-    if (e == cudaSuccess) e = proj_tc_setup();
-    if (e == cudaSuccess) e = proj_tc2_setup();
     if (e == cudaSuccess) e = proj_tc3_setup();
+    if (e == cudaSuccess) e = proj_h_setup();
     if (e == cudaSuccess) e = rec_tc_setup();
+    if (e == cudaSuccess) e = rec_h_setup();
     if (const char* rt = getenv("ROKO_B200_REC_TC_MIN")) m->rec_tc_min = atoi(rt);
     if (const char* sb = getenv("ROKO_B200_SUPERBATCH")) m->superbatch = atoi(sb) > 0 ? atoi(sb) : 1;
-    {
-        const char* pj = getenv("ROKO_B200_PROJ");
-        if (pj && strcmp(pj, "ffma") == 0) m->use_tc = 0;
-        else if (pj && strcmp(pj, "tc1") == 0) m->use_tc = 1;
-        else if (pj && strcmp(pj, "tc2") == 0) m->use_tc = 2;
-        else m->use_tc = 3;
-    }
+    if (const char* pj = getenv("ROKO_B200_PROJ")) m->use_tc = strcmp(pj, "ffma") == 0 ? 0 : (strcmp(pj, "tf32") == 0 ? 3 : 4);
+    if (const char* rk = getenv("ROKO_B200_REC")) m->rec_kind = strcmp(rk, "tf32") == 0 ? 1 : 2;
+    if (const char* gr = getenv("ROKO_B200_GRAPHS")) m->use_graphs = atoi(gr);
     if (e != cudaSuccess) {
         roko_b200_model_destroy(m);
         return fail(ROKO_B200_ECUDA, "model_create: %s%s", cudaGetErrorString(e));
@@ -186,25 +272,19 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
 
 int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device, void* stream) {
     if (!m || !raw) return fail(ROKO_B200_EARG, "model / raw is NULL%s%s");
+    Range r("roko_b200_model_load");
     DeviceGuard g(m->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool on_device = raw_on_device & 1, no_sync = raw_on_device & 2;
     CU(cudaMemcpyAsync(m->raw_stage, raw, (size_t)RAW_TOTAL * sizeof(float),
-                       raw_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(m->raw_al, m->raw_stage, (size_t)RAW_GRU * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(m->raw_al + RAW_GRU + RAW_AL_PAD, m->raw_stage + RAW_GRU,
                        (size_t)(RAW_TOTAL - RAW_GRU) * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    CU(launch_pack(m->raw_stage, m->packed, s));
-    // W2 / b1 / b2 ride in the front-end kernel's parameter bank: keep a host copy
-    if (raw_on_device) {
-        CU(cudaMemcpyAsync(m->fc.W2, raw + RAW_W2, sizeof(m->fc.W2), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(m->fc.b1, raw + RAW_B1, sizeof(m->fc.b1), cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(m->fc.b2, raw + RAW_B2, sizeof(m->fc.b2), cudaMemcpyDeviceToHost, s));
-    } else {
-        memcpy(m->fc.W2, raw + RAW_W2, sizeof(m->fc.W2));
-        memcpy(m->fc.b1, raw + RAW_B1, sizeof(m->fc.b1));
-        memcpy(m->fc.b2, raw + RAW_B2, sizeof(m->fc.b2));
-    }
-    CU(cudaStreamSynchronize(s));
+    CU(launch_pack(m->raw_stage, m->packed, m->status, s));
+    // Every kernel reads its weights from `packed` (nothing rides in kernel parameters), so later work on
+    // the SAME stream needs no host synchronisation; work on other streams does (bit 1 of raw_on_device unset).
+    if (!no_sync) CU(cudaStreamSynchronize(s));
     m->loaded = true;
     return ROKO_B200_OK;
 }
@@ -217,6 +297,7 @@ int roko_b200_model_destroy(roko_b200_model* m) {
         if (sl.done) cudaEventDestroy(sl.done);
         cudaFree(sl.x); cudaFree(sl.labels); cudaFree(sl.logits); cudaFree(sl.ws);
     }
+    drop_graphs(m);
     cudaFree(m->packed); cudaFree(m->raw_stage); cudaFree(m->raw_al); cudaFree(m->train_img); cudaFree(m->status);
     delete m;
     return ROKO_B200_OK;
@@ -226,9 +307,16 @@ int roko_b200_forward_u8(roko_b200_model* m, const uint8_t* x, int n_windows, fl
                          uint8_t* labels, void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_common(m, x, n_windows, workspace)) return rc;
     if (n_windows == 0) return ROKO_B200_OK;
+    Range r("roko_b200_forward_u8");
     DeviceGuard g(m->device);
-    return run_forward(m, x, n_windows, logits, labels, workspace, workspace_bytes,
-                       static_cast<cudaStream_t>(stream), nullptr, WS_PER_WINDOW * sizeof(float));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t per = WS_PER_WINDOW * sizeof(float);
+    if (m->use_graphs && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
+        (size_t)n_windows * per <= workspace_bytes) {
+        const int rc = graph_forward(m, x, n_windows, logits, labels, workspace, s);
+        if (rc != GRAPH_UNAVAILABLE) return rc;
+    }
+    return run_forward(m, x, n_windows, logits, labels, workspace, workspace_bytes, s, nullptr, per);
 }
 
 int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, float* logits,
@@ -338,9 +426,16 @@ int roko_b200_measure_fp32_peak(int device, double* tflops) {
 
 int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long value) {
     if (!m || !name) return fail(ROKO_B200_EARG, "model / name is NULL%s%s");
+    {   // captured graphs bake the kernel choice in: start over
+        std::lock_guard<std::mutex> lock(m->mu);
+        drop_graphs(m);
+    }
     if (strcmp(name, "rec_tc_min") == 0) { m->rec_tc_min = (int)value; return ROKO_B200_OK; }
     if (strcmp(name, "superbatch") == 0) { if (value < 1) return fail(ROKO_B200_EARG, "superbatch < 1%s%s"); m->superbatch = (int)value; return ROKO_B200_OK; }
-    if (strcmp(name, "proj") == 0) { if (value < 0 || value > 3) return fail(ROKO_B200_EARG, "proj must be 0..3%s%s"); m->use_tc = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "proj") == 0) { if (value != 0 && value != 3 && value != 4) return fail(ROKO_B200_EARG, "proj must be 0 (ffma), 3 (tf32) or 4 (fp16)%s%s"); m->use_tc = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "rec") == 0) { if (value != 1 && value != 2) return fail(ROKO_B200_EARG, "rec must be 1 (tf32) or 2 (fp16)%s%s"); m->rec_kind = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "graphs") == 0) { m->use_graphs = value != 0; return ROKO_B200_OK; }
+    if (strcmp(name, "front") == 0) { if (value != 0 && value != 1) return fail(ROKO_B200_EARG, "front must be 0 (mma.sync) or 1 (tcgen05)%s%s"); m->front_kind = (int)value; return ROKO_B200_OK; }
     return fail(ROKO_B200_EARG, "unknown option '%s'%s", name);
 }
 
@@ -352,7 +447,9 @@ int roko_b200_model_check(roko_b200_model* m) {
     CU(cudaMemcpy(&st, m->status, sizeof(int), cudaMemcpyDeviceToHost));
     if (st) {
         CU(cudaMemset(m->status, 0, sizeof(int)));
-        return fail(ROKO_B200_ECODES, "input code outside 0..11 (index out of range in embedding)%s%s");
+        if (st & 1) return fail(ROKO_B200_ECODES, "input code outside 0..11 (index out of range in embedding)%s%s");
+        if (st & 2) return fail(ROKO_B200_ERANGE, "a GRU weight is outside the fp16-split range (|w| >= 253): set option proj=3, rec=1 (tf32 kernels)%s%s");
+        return fail(ROKO_B200_ERANGE, "an activation left the fp16-split range (|u| >= 4062): set option proj=3 (tf32 kernel)%s%s");
     }
     return ROKO_B200_OK;
 }

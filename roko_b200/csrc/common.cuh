@@ -98,15 +98,21 @@ __host__ __device__ constexpr int pk_wtc(int l) {
 constexpr int RTC_W = G3 * HID;                  // 49 152
 constexpr int RTC_DIR = 2 * RTC_W + HID;         // floats per direction
 __host__ __device__ constexpr int pk_rtc(int l, int d) { return pk_wtc(LAYERS) + (l * 2 + d) * RTC_DIR; }
-// W_ih images for proj_tc2.cu: [n_tile][k_block of 16][hi|lo][256 rows x 16 floats], 64-byte swizzle
-constexpr int T2_IMG = 256 * 16;                 // floats in one hi (or lo) image: 16 KB
-__host__ __device__ constexpr int pk_wt2_size(int l) { return (GI_N / 256) * (gru_inp(l) / 16) * 2 * T2_IMG; }
-__host__ __device__ constexpr int pk_wt2(int l) {
+// fp16-split operands (tc.cuh) -- the default kernels:
+//   WH16 (proj_h.cu)  W_ih x 256 as fp16 hi / lo shared-memory images  [n_tile 3][k block of 64][hi|lo][256 rows x 128 B, SWIZZLE_128B]
+//   RH16 (rec_h.cu)   W_hh x 256 as fp16 hi / lo tensor-memory images  [gate tile 3][hi|lo][row 128][64 words: k = 2c, 2c+1], then b_hn[128]
+constexpr int H16_BK = 64;                       // fp16 elements per k block (one 128-byte swizzle row)
+constexpr int H16_IMG = TC_BN * H16_BK / 2;      // floats in one hi (or lo) image of 256 rows: 32 KB
+__host__ __device__ constexpr int pk_wh16_size(int l) { return (GI_N / TC_BN) * (gru_inp(l) / H16_BK) * 2 * H16_IMG; }
+__host__ __device__ constexpr int pk_wh16(int l) {
     int off = pk_rtc(LAYERS, 0);
-    for (int i = 0; i < l; ++i) off += pk_wt2_size(i);
+    for (int i = 0; i < l; ++i) off += pk_wh16_size(i);
     return off;
 }
-constexpr int PK_TOTAL = pk_wt2(LAYERS);
+constexpr int RH16_W = 3 * 2 * HID * (HID / 2);  // 49 152 words
+constexpr int RH16_DIR = RH16_W + HID;
+__host__ __device__ constexpr int pk_rh16(int l, int d) { return pk_wh16(LAYERS) + (l * 2 + d) * RH16_DIR; }
+constexpr int PK_TOTAL = pk_rh16(LAYERS, 0);
 
 // ---- workspace per window (floats) ------------------------------------------------------------
 constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
@@ -114,29 +120,23 @@ constexpr size_t WS_GI = (size_t)COLS * GI_N;    // input projection of one laye
 constexpr size_t WS_H = (size_t)COLS * OUT_W;    // one layer's output; two buffers ping-pong
 constexpr size_t WS_PER_WINDOW = WS_U + WS_GI + 2 * WS_H;
 
-// small parameters that live in the kernel-parameter constant bank of the front-end kernel
-struct FrontConst {
-    float W2[FC2 * FC1];   // [k][j]
-    float b1[FC1];
-    float b2[FC2];
-};
-
 // ---- launchers (one per translation unit) ------------------------------------------------------
-cudaError_t launch_pack(const float* raw, float* packed, cudaStream_t s);
+cudaError_t launch_pack(const float* raw, float* packed, int* status, cudaStream_t s);
 cudaError_t launch_narrow_i64(const long long* x64, uint8_t* x8, size_t n, int* status, cudaStream_t s);
-cudaError_t launch_front(const FrontConst& fc, const uint8_t* x, const float* packed, float* u, int nwin,
+cudaError_t launch_front(const uint8_t* x, const float* packed, float* u, int nwin,
                          int* status, int num_sms, cudaStream_t s);
 cudaError_t launch_proj(const float* A, int K, const float* W, const float* bias, float* C, int M,
                         cudaStream_t s);
-cudaError_t launch_proj_tc(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
-                           cudaStream_t s);
-cudaError_t proj_tc_setup();
-cudaError_t launch_proj_tc2(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
-                            cudaStream_t s);
-cudaError_t proj_tc2_setup();
 cudaError_t launch_proj_tc3(const float* A, int K, const float* wimg, const float* bias, float* C, int M,
                             int num_sms, cudaStream_t s);
 cudaError_t proj_tc3_setup();
+// fp16-split projection (proj_h.cu): in_scale = power-of-two scale applied to A before the split (tc::U_SCALE / tc::H_SCALE)
+cudaError_t launch_proj_h(const float* A, int K, const float* wimg, const float* bias, float* C, int M, float in_scale,
+                          int* status, int num_sms, cudaStream_t s);
+cudaError_t proj_h_setup();
+// fp16-split recurrence (rec_h.cu): rh16_d0 = pk_rh16(l, 0), directions RH16_DIR floats apart
+cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, cudaStream_t s);
+cudaError_t rec_h_setup();
 cudaError_t launch_rec_tc(const float* gi, const float* whi_d0, const float* wlo_d0, size_t dir_stride,
                           const float* bhn_d0, float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t rec_tc_setup();

@@ -157,7 +157,7 @@ __device__ __forceinline__ void build_m(const float* w1t, const FrontList& W, fl
 }
 
 __global__ void __launch_bounds__(FR_THREADS, 1)
-front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x,
+front_kernel(const uint8_t* __restrict__ x,
              const float* __restrict__ packed, float* __restrict__ u, int nwin, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FrontSmem& S = *reinterpret_cast<FrontSmem*>(smem_raw);
@@ -185,7 +185,7 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
     }
     for (int i = tid; i < FC2 * FC1P; i += FR_THREADS) {
         const int k = i / FC1P, j = i % FC1P;
-        const float v = j < FC1 ? P.W2[k * FC1 + j] : 0.f;
+        const float v = j < FC1 ? packed[PK_W2 + k * FC1 + j] : 0.f;
         if (k < 8) {
             const float hi = tf32r(v);
             S.w2h[k][j] = hi;
@@ -194,8 +194,8 @@ front_kernel(const __grid_constant__ FrontConst P, const uint8_t* __restrict__ x
             S.w2f[k - 8][j] = v;
         }
     }
-    for (int i = tid; i < FC1P; i += FR_THREADS) S.b1p[i] = i < FC1 ? P.b1[i] : 0.f;
-    if (tid < 16) S.b2p[tid] = tid < FC2 ? P.b2[tid] : 0.f;
+    for (int i = tid; i < FC1P; i += FR_THREADS) S.b1p[i] = i < FC1 ? packed[PK_B1 + i] : 0.f;
+    if (tid < 16) S.b2p[tid] = tid < FC2 ? packed[PK_B2 + tid] : 0.f;
     __syncthreads();
     auto fetch_window = [&](int w) {               // one thread: TMA bulk copy of a whole window
         const uint32_t bar = fr_smem_u32(&S.xbar);
@@ -345,11 +345,11 @@ cudaError_t front_setup() {
                                 (int)sizeof(FrontSmem) + 128);
 }
 
-cudaError_t launch_front(const FrontConst& fc, const uint8_t* x, const float* packed, float* u, int nwin,
+cudaError_t launch_front(const uint8_t* x, const float* packed, float* u, int nwin,
                          int* status, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
     int grid = nwin < num_sms ? nwin : num_sms;
-    front_kernel<<<grid, FR_THREADS, sizeof(FrontSmem) + 128, s>>>(fc, x, packed, u, nwin, status);
+    front_kernel<<<grid, FR_THREADS, sizeof(FrontSmem) + 128, s>>>(x, packed, u, nwin, status);
     return cudaGetLastError();
 }
 

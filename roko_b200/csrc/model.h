@@ -1,7 +1,11 @@
 // Private definition of the opaque roko_b200_model handle (include/roko_b200.h), shared by api.cu
 // and train_api.cu.
 #pragma once
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 constexpr int NSLOT = 3;
 constexpr int ROKO_ERRBUF = 512;
@@ -19,11 +23,13 @@ struct roko_b200_model {
                                     // (4 is measured slower: 11 520-row reductions leave too little work per 32 K-atomic tile epilogue)
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
-    int use_tc = 3;                 // projection: 3 = persistent tcgen05, double-buffered accumulators (proj_tc3.cu, default);
-                                    // ROKO_B200_PROJ=tc2 -> 256x256 tile, tc1 -> 128x256 tile, ffma -> FFMA SGEMM
+    int use_tc = 4;                 // projection: 4 = tcgen05, fp16-split operands (proj_h.cu, default); 3 = tcgen05 3xTF32
+                                    // (proj_tc3.cu); 0 = FFMA SGEMM (proj.cu, the fp32-exact A/B reference).  ROKO_B200_PROJ=fp16|tf32|ffma
+    int rec_kind = 2;               // tensor-core recurrence: 2 = fp16-split, W_hh resident in tensor memory (rec_h.cu, default);
+                                    // 1 = 3xTF32 (rec_tc.cu).  ROKO_B200_REC=fp16|tf32
     int superbatch = 2368;          // windows per device pass of infer_host (148 SMs x 16; ROKO_B200_SUPERBATCH)
-    int rec_tc_min = 256;           // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never)
-    roko::FrontConst fc;
+    int rec_tc_min = 64;            // chunks of at least this many windows use the tcgen05 recurrence (ROKO_B200_REC_TC_MIN; 0 = never);
+                                    // smaller ones the register-resident FFMA recurrence (rec.cu), which spreads few windows over many SMs
     struct Slot {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -33,6 +39,27 @@ struct roko_b200_model {
         void* ws = nullptr;
     } slot[NSLOT];
     int slot_cap = 0;
+    // CUDA-graph instances of the forward chain (api.cu: graph_forward)
+    struct GraphEntry {
+        int n = 0;
+        const void* ws = nullptr;
+        bool want_logits = false, want_labels = false;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t front = nullptr, head = nullptr;
+        cudaKernelNodeParams fp{}, hp{};
+        void* fargs[5] = {};
+        void* hargs[6] = {};
+        const uint8_t* x = nullptr;       // the per-launch values the patched parameters point at
+        float* logits = nullptr;
+        uint8_t* labels = nullptr;
+        unsigned long long last_use = 0;
+    };
+    std::vector<GraphEntry*> graphs;
+    std::mutex mu;
+    unsigned long long graph_clock = 0;
+    int use_graphs = 1;             // replay the chain as a CUDA graph when the batch fits the workspace (ROKO_B200_GRAPHS=0 disables)
+    int front_kind = 0;             // front end: 0 = warp-level mma.sync stages (front.cu); 1 = tcgen05 stages (front_tc.cu)
 };
 
 // offset of raw element `off` inside raw_al (RAW_GRU is 2 mod 4 and every later tensor size is a multiple of 4)
@@ -45,8 +72,22 @@ inline cudaError_t proj_dispatch(const roko_b200_model* m, const float* in, int 
                                  cudaStream_t s) {
     using namespace roko;
     const float* pk = m->packed;
+    if (m->use_tc == 4)
+        return launch_proj_h(in, gru_inp(l), pk + pk_wh16(l), pk + pk_bgi(l), gi, rows, l == 0 ? tc::U_SCALE : tc::H_SCALE,
+                             m->status, m->num_sms, s);
     if (m->use_tc == 3) return launch_proj_tc3(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, m->num_sms, s);
-    if (m->use_tc == 2) return launch_proj_tc2(in, gru_inp(l), pk + pk_wt2(l), pk + pk_bgi(l), gi, rows, s);
-    if (m->use_tc) return launch_proj_tc(in, gru_inp(l), pk + pk_wtc(l), pk + pk_bgi(l), gi, rows, s);
     return launch_proj(in, gru_inp(l), pk + pk_wih(l), pk + pk_bgi(l), gi, rows, s);
+}
+
+// Recurrence of GRU layer `l` over `nc` windows (both directions): tensor cores from rec_tc_min windows on.
+inline cudaError_t rec_dispatch(const roko_b200_model* m, const float* gi, int l, float* out, int nc, cudaStream_t s) {
+    using namespace roko;
+    const float* pk = m->packed;
+    if (m->rec_tc_min > 0 && nc >= m->rec_tc_min) {
+        if (m->rec_kind == 2) return launch_rec_h(gi, pk + pk_rh16(l, 0), out, nc, m->num_sms, s);
+        if (nc >= 64)       // (>= 64 windows keeps rec_tc's unguarded gi reads of a ragged last group inside the scratch)
+            return launch_rec_tc(gi, pk + pk_rtc(l, 0), pk + pk_rtc(l, 0) + RTC_W, (size_t)RTC_DIR, pk + pk_rtc(l, 0) + 2 * RTC_W,
+                                 out, nc, m->num_sms, s);
+    }
+    return launch_rec(gi, pk + pk_whh(l, 0), (size_t)(pk_whh(0, 1) - pk_whh(0, 0)), pk + pk_bhn(l, 0), out, nc, m->num_sms, s);
 }

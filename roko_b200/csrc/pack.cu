@@ -1,10 +1,11 @@
 // Weight packing: raw state_dict order -> the layouts the kernels read.
 // One thread per packed float; runs once per load_state_dict (reference inference.py:95).
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace roko {
 
-__device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) {
+__device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p, int* __restrict__ status) {
     if (p < PK_W1T) return p < NCODES * EMB ? raw[RAW_E + p] : 0.f;
     if (p < PK_B1) {                                   // W1T[r][j] = fc1.weight[j][r]; row 200 = 0
         int i = p - PK_W1T;
@@ -49,29 +50,45 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) 
     }
     if (p < PK_B4) { int i = p - PK_W4; return i < CLASSES * OUT_W ? raw[RAW_W4 + i] : 0.f; }
     if (p < pk_wtc(0)) { int i = p - PK_B4; return i < CLASSES ? raw[RAW_B4 + i] : 0.f; }
-    if (p >= pk_wt2(0)) {      // tf32 hi/lo images of W_ih, 64-byte swizzle, 16-float k-blocks (proj_tc2.cu)
-        int l = 0;
-        while (l + 1 < LAYERS && p >= pk_wt2(l + 1)) ++l;
-        const int kin = gru_in(l), kblocks = gru_inp(l) / 16;
-        int i = p - pk_wt2(l);
-        const int ntile = i / (kblocks * 2 * T2_IMG);
-        i %= kblocks * 2 * T2_IMG;
-        const int kb = i / (2 * T2_IMG);
-        i %= 2 * T2_IMG;
-        const int half = i / T2_IMG;
-        const int ob = (i % T2_IMG) * 4;                 // byte offset inside the 16 KB image
-        const int rgrp = ob / 512, within = ob % 512;
-        const int r8 = within / 64, pchunk = (within % 64) / 16, w4 = (within % 16) / 4;
-        const int r = rgrp * 8 + r8;
-        const int kk = ((pchunk ^ ((r8 >> 1) & 3)) * 4) + w4;      // undo the 64B swizzle
-        const int k = kb * 16 + kk;
-        const int n = ntile * 256 + r;
+    if (p >= pk_wh16(0)) {     // fp16-split operands of the default kernels (tc.cuh): two halves per packed word
+        auto pair = [&](float v0, float v1, bool lo) -> float {
+            v0 *= tc::W_SCALE; v1 *= tc::W_SCALE;
+            if (fabsf(v0) > 65000.f || fabsf(v1) > 65000.f) atomicOr(status, 2);       // outside fp16's range: see roko_b200_model_check
+            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+            const __half a = lo ? __float2half_rn(v0 - __half2float(h0)) : h0;
+            const __half b = lo ? __float2half_rn(v1 - __half2float(h1)) : h1;
+            return __uint_as_float((uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16));
+        };
+        if (p >= pk_rh16(0, 0)) {                      // rec_h.cu: W_hh [gate tile][hi|lo][row][word c: k = 2c, 2c+1], b_hn
+            int i = p - pk_rh16(0, 0);
+            const int ld = i / RH16_DIR, l = ld / 2, d = ld % 2;
+            i %= RH16_DIR;
+            if (i >= RH16_W) return raw[raw_bhh(l, d) + 2 * HID + (i - RH16_W)];
+            const int mt = i / (2 * HID * (HID / 2));
+            i %= 2 * HID * (HID / 2);
+            const bool lo = i >= HID * (HID / 2);
+            i %= HID * (HID / 2);
+            const int row = i / (HID / 2), c = i % (HID / 2);
+            const float* w = raw + raw_whh(l, d) + (mt * HID + row) * HID + 2 * c;
+            return pair(w[0], w[1], lo);
+        }
+        int l = 0;                                     // proj_h.cu: W_ih images, 128-byte swizzle, 64-element k blocks
+        while (l + 1 < LAYERS && p >= pk_wh16(l + 1)) ++l;
+        const int kin = gru_in(l), kblocks = gru_inp(l) / H16_BK;
+        int i = p - pk_wh16(l);
+        const int ntile = i / (kblocks * 2 * H16_IMG);
+        i %= kblocks * 2 * H16_IMG;
+        const int kb = i / (2 * H16_IMG);
+        i %= 2 * H16_IMG;
+        const bool lo = i >= H16_IMG;
+        const int ob = (i % H16_IMG) * 4;                // byte offset inside the 32 KB image
+        const int rgrp = ob / 1024, within = ob % 1024;
+        const int r8 = within / 128, pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+        const int k = kb * H16_BK + ((pchunk ^ r8) * 8) + w4 * 2;
+        const int n = ntile * TC_BN + rgrp * 8 + r8;
         const int d = n / G3, j = (n % G3) / 3, g = (n % G3) % 3;
-        const float v = k < kin ? raw[raw_wih(l, d) + (g * HID + j) * kin + k] : 0.f;
-        unsigned hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-        const float hi = __uint_as_float(hb);
-        return half == 0 ? hi : v - hi;
+        const float* w = raw + raw_wih(l, d) + (g * HID + j) * kin;
+        return pair(k < kin ? w[k] : 0.f, k + 1 < kin ? w[k + 1] : 0.f, lo);
     }
     if (p >= pk_rtc(0, 0)) {   // tensor-core recurrence operands (rec_tc.cu)
         int i = p - pk_rtc(0, 0);
@@ -121,9 +138,9 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p) 
     }
 }
 
-__global__ void pack_kernel(const float* __restrict__ raw, float* __restrict__ packed) {
+__global__ void pack_kernel(const float* __restrict__ raw, float* __restrict__ packed, int* __restrict__ status) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < PK_TOTAL) packed[p] = pack_one(raw, p);
+    if (p < PK_TOTAL) packed[p] = pack_one(raw, p, status);
 }
 
 // int64 codes (what the reference caller passes, inference.py:113) -> uint8; flags codes > 11
@@ -185,8 +202,8 @@ cudaError_t measure_fp32_peak(double* tflops) {
     return e;
 }
 
-cudaError_t launch_pack(const float* raw, float* packed, cudaStream_t s) {
-    pack_kernel<<<(PK_TOTAL + 255) / 256, 256, 0, s>>>(raw, packed);
+cudaError_t launch_pack(const float* raw, float* packed, int* status, cudaStream_t s) {
+    pack_kernel<<<(PK_TOTAL + 255) / 256, 256, 0, s>>>(raw, packed, status);
     return cudaGetLastError();
 }
 

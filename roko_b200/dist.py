@@ -70,7 +70,14 @@ def gather_labels(local_labels, n_total, group=None, dst=0):
     return torch.cat([recv[r * cap:r * cap + sizes[r]] for r in range(world)])
 
 
-def average_gradients(module, group=None):
+def sum_gradients(module, group=None):
+    """Like ``average_gradients`` without the division: for losses already normalised by the GLOBAL batch
+    (sum over local positions / global position count), the all-reduced SUM is the gradient of the global mean --
+    also when shards are ragged or empty.  Returns the number of bytes reduced."""
+    return average_gradients(module, group=group, divide=False)
+
+
+def average_gradients(module, group=None, divide=True):
     """Data-parallel training step, reference roko/train.py:46-53 over several ranks: every rank ran
     forward/backward on its share of the batch; one flat all-reduce (4.4 MB for this network, NCCL
     over NVLink on GPUs) leaves the mean gradient in every ``param.grad``.  Parameters without a
@@ -82,7 +89,8 @@ def average_gradients(module, group=None):
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).detach().reshape(-1).to(torch.float32)
                       for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(world)
+    if divide:
+        flat.div_(world)
     off = 0
     for p in params:
         n = p.numel()

@@ -2,6 +2,7 @@
 and ``.pth`` weight formats, same FASTA output), with the model call replaced by the B200 path.
 
     python -m roko_b200.inference <data.hdf5> <model.pth> <out.fasta> [--t workers] [--b batch]
+    torchrun --nproc-per-node 8 -m roko_b200.inference <data.hdf5> <model.pth> <out.fasta>      # windows sharded over 8 GPUs
 
 Reference behaviour mirrored (file:line in /root/reference/roko/inference.py):
   * alphabet / decoding                                              :14-17
@@ -185,6 +186,7 @@ def infer(data, model_path, out, workers=0, batch_size=128, h5=None, device=None
             if (i + 1) % 100 == 0:
                 print(f"{i + 1} batches processed")
 
+    model.check_codes()                       # nn.Embedding would have raised IndexError on a code outside 0..11
     records = []
     for contig in votes.tables:
         positions, winners = votes.consensus(contig)
@@ -194,55 +196,135 @@ def infer(data, model_path, out, workers=0, batch_size=128, h5=None, device=None
 
 
 class DenseVoteTable:
-    """Same ``Counter`` semantics as ``VoteTable`` but dense and in torch (CPU or CUDA tensors):
-    per contig ``counts[(rpos * 4 + ins), label]`` by scatter-add and the sequence number of each label's
-    first vote by scatter-amin; sized from the contig length (slots for rpos 0..len-1, ins 0..3)."""
+    """Same ``Counter`` semantics as ``VoteTable`` but dense and in torch (CPU or CUDA tensors): per contig
+    ``counts[(rpos - base) * 4 + ins, label]`` by scatter-add and the sequence number of each label's first vote by
+    scatter-amin.
 
-    def __init__(self, device):
+    A table covers only the position RANGE its contig's windows actually touch (it grows, with slack, when a
+    later group reaches outside), costs 60 B per slot (240 B per draft base in range), and is dropped by
+    ``release`` once the contig is stitched -- so the footprint follows the contig being processed, not the
+    genome.  A contig whose range would exceed ``budget_bytes`` is handed to the sparse ``VoteTable`` instead
+    (the reference's Counter path has no such limit either: roko/inference.py:101)."""
+
+    SLOT_BYTES = N_LABELS * (4 + 8)
+
+    def __init__(self, device, budget_bytes=4 << 30):
         self.device = torch.device(device)
         self.tables = {}
+        self.sparse = VoteTable()
         self.seq = 0
+        self.budget = int(budget_bytes)
 
-    def add(self, contig, contig_len, pos, labels):
-        """pos (n,2) int64 tensor [(rpos, ins)], labels (n,) uint8 tensor, in window/position order."""
-        t = self.tables.get(contig)
-        if t is None:
-            slots = int(contig_len) * (MAX_INS + 1)
-            t = self.tables[contig] = {
+    def _alloc(self, base, span):
+        slots = span * (MAX_INS + 1)
+        return {"base": base, "span": span,
                 "counts": torch.zeros(slots * N_LABELS, dtype=torch.int32, device=self.device),
                 "first": torch.full((slots * N_LABELS,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=self.device)}
+
+    def _cover(self, contig, lo, hi):
+        """Make contig's table cover reference positions [lo, hi]; returns it, or None once the contig is sparse."""
+        t = self.tables.get(contig)
+        if t is None and contig in self.sparse.tables:
+            return None
+        if t is not None and t["base"] <= lo and hi < t["base"] + t["span"]:
+            return t
+        nlo = lo if t is None else min(lo, t["base"])
+        nhi = hi if t is None else max(hi, t["base"] + t["span"] - 1)
+        slack = 0 if t is None else max(1 << 16, (nhi - nlo + 1) // 2)          # amortise growth in file order
+        nlo2, nhi2 = (nlo, nhi + slack) if t is None or lo >= t["base"] else (max(0, nlo - slack), nhi)
+        span = nhi2 - nlo2 + 1
+        if span * (MAX_INS + 1) * self.SLOT_BYTES > self.budget:
+            self._spill(contig)
+            return None
+        n = self._alloc(nlo2, span)
+        if t is not None:
+            off = (t["base"] - nlo2) * (MAX_INS + 1) * N_LABELS
+            n["counts"][off:off + t["counts"].numel()] = t["counts"]
+            n["first"][off:off + t["first"].numel()] = t["first"]
+        self.tables[contig] = n
+        return n
+
+    def _spill(self, contig):
+        """Move a contig to the sparse table (keeps counts and first-vote order)."""
+        t = self.tables.pop(contig, None)
+        st = self.sparse.tables.setdefault(contig, {"keys": np.empty(0, np.int64), "counts": np.zeros((0, N_LABELS), np.int32),
+                                                    "first": np.zeros((0, N_LABELS), np.int64)})
+        if t is not None:
+            counts = t["counts"].view(-1, N_LABELS)
+            voted = torch.nonzero(counts.sum(dim=1) > 0)[:, 0]
+            st["keys"] = (voted + t["base"] * (MAX_INS + 1)).cpu().numpy()
+            st["counts"] = counts[voted].cpu().numpy()
+            st["first"] = t["first"].view(-1, N_LABELS)[voted].cpu().numpy()
+
+    def add(self, contig, contig_len, pos, labels):
+        """pos (n,2) int64 tensor [(rpos, ins)], labels (n,) uint8 tensor, in window/position order.
+        ``contig_len`` is informative only: tables are sized from the positions themselves."""
+        n = labels.numel()
+        if n == 0:
+            return
+        pos = torch.as_tensor(pos)
+        if int(pos[:, 1].max()) > MAX_INS or int(pos.min()) < 0:
+            raise IndexError("position outside (rpos >= 0, 0 <= ins <= %d)" % MAX_INS)
+        lo, hi = int(pos[:, 0].min()), int(pos[:, 0].max())
+        t = self._cover(contig, lo, hi)
+        if t is None:                                                     # sparse contig: numpy path, shared sequence numbers
+            self.sparse.seq = self.seq
+            self.sparse.add(contig, pos.cpu().numpy(), labels.cpu().numpy())
+            self.seq += n
+            return
         pos = pos.to(self.device, torch.int64)
-        idx = (pos[:, 0] * (MAX_INS + 1) + pos[:, 1]) * N_LABELS + labels.to(self.device, torch.int64)
+        idx = ((pos[:, 0] - t["base"]) * (MAX_INS + 1) + pos[:, 1]) * N_LABELS + labels.to(self.device, torch.int64)
         t["counts"].scatter_add_(0, idx, torch.ones_like(idx, dtype=torch.int32))
-        order = torch.arange(self.seq, self.seq + idx.numel(), dtype=torch.int64, device=self.device)
+        order = torch.arange(self.seq, self.seq + n, dtype=torch.int64, device=self.device)
         t["first"].scatter_reduce_(0, idx, order, reduce="amin", include_self=True)
-        self.seq += idx.numel()
+        self.seq += n
+
+    def contigs(self):
+        return list(dict.fromkeys(list(self.tables) + list(self.sparse.tables)))
 
     def consensus(self, contig):
-        t = self.tables[contig]
+        t = self.tables.get(contig)
+        if t is None:
+            return self.sparse.consensus(contig)
         counts = t["counts"].view(-1, N_LABELS)
         first = t["first"].view(-1, N_LABELS)
         best = counts.max(dim=1, keepdim=True).values
         voted = torch.nonzero(best[:, 0] > 0)[:, 0]
         cand = torch.where(counts[voted] == best[voted], first[voted], torch.full_like(first[voted], torch.iinfo(torch.int64).max))
         winner = cand.argmin(dim=1)
-        keys = voted.cpu().numpy()
+        keys = voted.cpu().numpy() + t["base"] * (MAX_INS + 1)
         return np.stack([keys // (MAX_INS + 1), keys % (MAX_INS + 1)], axis=1), winner.cpu().numpy()
+
+    def release(self, contig):
+        self.tables.pop(contig, None)
+        self.sparse.tables.pop(contig, None)
 
 
 class _SlabDataset(Dataset):
-    """One item = up to ``chunk`` consecutive windows of one group, read as slabs (row f3 of SURVEY.md 8f)."""
+    """One item = up to ``chunk`` consecutive windows of one group, read as slabs (row f3 of SURVEY.md 8f).
 
-    def __init__(self, path, chunk, h5=None):
-        self.path, self.chunk, self._h5mod, self.fd = path, chunk, h5, None
-        self.items, self.contigs = [], {}
+    ``lo``/``hi`` restrict the dataset to the flat window range [lo, hi) (multi-GPU sharding: contiguous ranges
+    keep labels aligned with the positions the stitcher needs, roko/inference.py:119-124); ``examples=False``
+    reads positions only (rank 0 of a sharded run votes with labels gathered from the other ranks)."""
+
+    def __init__(self, path, chunk, h5=None, lo=0, hi=None, examples=True):
+        self.path, self.chunk, self._h5mod, self.fd, self.examples = path, chunk, h5, None, examples
+        self.items, self.contigs, self.group_contig, self.total = [], {}, {}, 0
         fd = self._open()
         try:
+            flat = 0
             for g in fd.keys():
                 if g == "contigs":
                     continue
                 n = int(fd[g].attrs["size"])
-                self.items.extend((g, a, min(a + chunk, n)) for a in range(0, n, chunk))
+                self.group_contig[g] = fd[g].attrs["contig"]
+                for a in range(0, n, chunk):
+                    b = min(a + chunk, n)
+                    a2, b2 = max(a, lo - flat), (b if hi is None else min(b, hi - flat))
+                    if a2 < b2:
+                        self.items.append((g, a2, b2, flat + a2))
+                flat += n
+            self.total = flat
             for k in fd["contigs"]:
                 grp = fd["contigs"][k]
                 self.contigs[str(k)] = (grp.attrs["seq"], grp.attrs["len"])
@@ -258,42 +340,95 @@ class _SlabDataset(Dataset):
     def __getitem__(self, i):
         if self.fd is None:
             self.fd = self._open()
-        g, a, b = self.items[i]
+        g, a, b, flat = self.items[i]
         grp = self.fd[g]
-        return (grp.attrs["contig"], torch.from_numpy(np.ascontiguousarray(grp["positions"][a:b])),
-                torch.from_numpy(np.ascontiguousarray(grp["examples"][a:b])))
+        x = torch.from_numpy(np.ascontiguousarray(grp["examples"][a:b])) if self.examples else torch.empty(0)
+        return grp.attrs["contig"], torch.from_numpy(np.ascontiguousarray(grp["positions"][a:b])), x, flat
 
 
-def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device=None, chunk=8192):
-    """Throughput driver: slab reads -> predict_host (coalesced device passes) -> dense GPU vote -> stitch."""
+def _dist_env():
+    import os
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device=None, chunk=8192, vote_budget=4 << 30):
+    """Throughput driver: slab reads -> predict_host (coalesced device passes) -> dense GPU vote -> stitch.
+
+    Launched under ``torchrun`` (WORLD_SIZE > 1, one process per GPU) it shards the flat window range into contiguous
+    per-rank ranges, broadcasts the weights from rank 0 over NCCL (one flat 4.4 MB broadcast instead of the
+    reference's dormant per-forward ``nn.DataParallel`` replication, roko/inference.py:12,96-97), gathers the uint8
+    labels (90 B / window) to rank 0 over NVLink, and rank 0 votes, stitches and writes the FASTA.  Returns the
+    records on rank 0 and ``None`` elsewhere."""
     if not torch.cuda.is_available():
         raise RuntimeError("roko_b200.inference needs a CUDA (sm_100a) device: the model path has no CPU fallback")
-    device = torch.device(device or "cuda:0")
+    rank, local_rank, world = _dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        from . import dist as rdist
+        device = torch.device("cuda", local_rank)
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+    else:
+        device = torch.device(device or "cuda:0")
     model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)
-    model.load_state_dict(torch.load(model_path, map_location=device))
+    if rank == 0:
+        model.load_state_dict(torch.load(model_path, map_location=device))
+    if world > 1:
+        rdist.broadcast_weights(model, src=0)
     model.eval()
 
-    dataset = _SlabDataset(data, chunk, h5=h5)
+    meta = _SlabDataset(data, chunk, h5=h5, examples=False)                # full index (positions only)
+    lo, hi = (0, meta.total) if world == 1 else rdist.shard_range(meta.total, rank, world)
+    dataset = _SlabDataset(data, chunk, h5=h5, lo=lo, hi=hi)
     loader = DataLoader(dataset, batch_size=None, shuffle=False, num_workers=workers)
-    votes = DenseVoteTable(device)
     x_pin = torch.empty((chunk, 200, 90), dtype=torch.uint8).pin_memory()
     y_pin = torch.empty((chunk, 90), dtype=torch.uint8).pin_memory()
-    print("Inference started")
+    votes = DenseVoteTable(device, budget_bytes=vote_budget) if rank == 0 else None
+    remaining = {}                                                        # items still to vote per contig (rank 0)
+    for g, a, b, _ in meta.items:
+        remaining[meta.group_contig[g]] = remaining.get(meta.group_contig[g], 0) + 1
+    records, order = {}, []
+
+    def vote(contig, pos, labels):
+        if contig not in remaining:
+            return
+        if contig not in order:
+            order.append(contig)
+        votes.add(contig, meta.contigs[contig][1], pos.reshape(-1, 2), labels.reshape(-1))
+        remaining[contig] -= 1
+        if remaining[contig] == 0:                                        # contig complete: stitch now, free its table
+            positions, winners = votes.consensus(contig)
+            records[contig] = stitch(meta.contigs[contig][0], positions, winners)
+            votes.release(contig)
+
+    if rank == 0:
+        print("Inference started")
+    local = torch.empty((hi - lo, 90), dtype=torch.uint8, device=device) if world > 1 else None
     done = 0
-    for contig, pos, x in loader:
+    for contig, pos, x, flat in loader:
         n = x.shape[0]
         x_pin[:n].copy_(x)
         model.predict_host(x_pin[:n], batch=batch_size, out=y_pin[:n], device=device)
-        votes.add(contig, dataset.contigs[contig][1], pos.reshape(-1, 2), y_pin[:n].reshape(-1))
+        if world > 1:
+            local[flat - lo:flat - lo + n].copy_(y_pin[:n])
+        else:
+            vote(contig, pos, y_pin[:n])
         done += n
-        if (done // batch_size) % 100 == 0:
+        if rank == 0 and (done // batch_size) % 100 == 0:
             print(f"{done // batch_size} batches processed")
-    records = []
-    for contig in votes.tables:
-        positions, winners = votes.consensus(contig)
-        records.append((contig, stitch(dataset.contigs[contig][0], positions, winners)))
-    write_fasta(records, out)
-    return records
+    model.check_codes()                                                   # nn.Embedding would have raised on a bad code
+    if world > 1:
+        labels = rdist.gather_labels(local, meta.total)                   # (N, 90) uint8 on rank 0, rank order = file order
+        if rank != 0:
+            return None
+        labels = labels.cpu()
+        for i in range(len(meta)):
+            contig, pos, _, flat = meta[i]
+            vote(contig, pos, labels[flat:flat + pos.shape[0]])
+    out_records = [(c, records[c]) for c in order]
+    write_fasta(out_records, out)
+    return out_records
 
 
 def main():

@@ -39,12 +39,16 @@ MAX_TRAIN_BATCH = 1024    # windows per training forward/backward (8.1 MB of sav
 
 
 def gru_init(gru):
-    """Initialisation the reference applies to its GRU (roko/rnn_model.py:15-21)."""
-    for p in gru.parameters():
-        if p.dim() >= 2:
-            init.orthogonal_(p.data)
-        else:
-            init.normal_(p.data)
+    """Initialisation the reference applies to its GRU (roko/rnn_model.py:15-21).
+
+    Written through the parameter itself under ``no_grad`` (not ``p.data``) so the in-place update bumps
+    the tensor version the packed-weight cache watches."""
+    with torch.no_grad():
+        for p in gru.parameters():
+            if p.dim() >= 2:
+                init.orthogonal_(p)
+            else:
+                init.normal_(p)
 
 
 def state_keys():
@@ -63,7 +67,7 @@ class _Handle:
         self.ptr = _cabi.c_model_p()
         _cabi.check(self.lib.roko_b200_model_create(ctypes.byref(self.ptr), device_index))
         self.device_index = device_index
-        self.version = None
+        self.version = None          # (weights epoch, sum of tensor versions, first data_ptr) the packed copy was made from
         self.workspaces = {}
 
     def __del__(self):
@@ -104,7 +108,7 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x8, p_drop, seed, *params):
-        h = module._handle(x8.device)
+        h = module._handle(x8.device, force=module.training)     # train mode: always re-pack (``.data`` writes are invisible)
         n, idx = x8.shape[0], h.device_index
         stream = torch.cuda.current_stream(idx).cuda_stream
         tws = torch.empty(h.lib.roko_b200_train_workspace_bytes(n), dtype=torch.uint8, device=x8.device)
@@ -165,14 +169,40 @@ class RNN(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_handles"] = {}
+        state.pop("_param_list", None)
         return state
 
     # ---- packed-weight cache ------------------------------------------------------------------
+    # The kernels read a packed copy of the 31 tensors.  It is rebuilt when (a) any parameter's autograd
+    # version counter moved (optimizer steps, ``copy_``, ``load_state_dict``, in-place init under no_grad),
+    # (b) the module was moved/cast (``_apply``) or (c) ``invalidate()`` was called.  The one thing torch
+    # does not count is a write through ``param.data`` (``p.data.add_(..)``, ``init.*_(p.data)``): code that
+    # edits weights that way must call ``model.invalidate()`` before the next forward.  In train mode the
+    # copy is refreshed on every forward regardless, so optimisers that write through ``.data`` are safe.
     def _ordered_params(self):
-        sd = dict(self.named_parameters())
-        return [sd[k] for k in state_keys()]
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            sd = dict(self.named_parameters())
+            ps = [sd[k] for k in state_keys()]
+            self.__dict__["_param_list"] = ps
+        return ps
 
-    def _handle(self, device):
+    def invalidate(self):
+        """Force the next forward to re-pack the weights (needed after writes through ``param.data``)."""
+        self.__dict__["_weights_epoch"] = self.__dict__.get("_weights_epoch", 0) + 1
+        self.__dict__.pop("_param_list", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _handle(self, device, force=False):
         if device.type != "cuda":
             raise RuntimeError("roko_b200.RNN runs on CUDA (sm_100a) only; there is no CPU fallback. "
                                "Move the module and the input to a B200: model.to('cuda')")
@@ -181,16 +211,18 @@ class RNN(nn.Module):
         if h is None:
             h = self._handles[idx] = _Handle(idx)
         params = self._ordered_params()
-        for p in params:
-            if p.device.type != "cuda" or (p.device.index or 0) != idx:
-                raise RuntimeError(f"parameter on {p.device}, input on cuda:{idx}")
-        version = tuple((p.data_ptr(), p._version) for p in params)
-        if h.version != version:
+        version = (self.__dict__.get("_weights_epoch", 0), sum([p._version for p in params]), params[0].data_ptr())
+        if force or h.version != version:
+            for p in params:
+                if p.device.type != "cuda" or (p.device.index or 0) != idx:
+                    raise RuntimeError(f"parameter on {p.device}, input on cuda:{idx}")
             with torch.no_grad():
                 raw = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params]).contiguous()
             assert raw.numel() == h.lib.roko_b200_raw_weight_count()
             stream = torch.cuda.current_stream(idx).cuda_stream
-            _cabi.check(h.lib.roko_b200_model_load(h.ptr, raw.data_ptr(), 1, stream))
+            # inference loads synchronise (forwards may follow on other streams); the per-step reload of the
+            # training path stays asynchronous on the training stream (flag bit 1)
+            _cabi.check(h.lib.roko_b200_model_load(h.ptr, raw.data_ptr(), 3 if force else 1, stream))
             h.version = version
         return h
 
@@ -256,6 +288,8 @@ class RNN(nn.Module):
     def _train_forward(self, x, seed=None):
         x = self._check_input(x)
         if x.dtype != torch.uint8:
+            if x.numel() and (int(x.min()) < 0 or int(x.max()) > 11):      # a wrapping cast would hide e.g. 256 -> 0
+                raise IndexError("index out of range in embedding: pileup codes must be 0..11")
             x = x.to(torch.uint8)
         if x.shape[0] == 0:
             return torch.zeros((0, COLS, CLASSES), dtype=torch.float32, device=x.device)
@@ -314,12 +348,14 @@ class RNN(nn.Module):
         return t
 
     def set_option(self, name, value, device=None):
-        """Scheduling knobs of the C library (see include/roko_b200.h): rec_tc_min, superbatch, proj."""
+        """Scheduling / kernel-selection knobs of the C library (see include/roko_b200.h): rec_tc_min, superbatch,
+        proj (0 ffma, 3 tf32, 4 fp16), rec (1 tf32, 2 fp16), front (0 mma.sync, 1 tcgen05), graphs (0/1)."""
         dev = torch.device(device) if device is not None else next(self.parameters()).device
         h = self._handle(dev)
         _cabi.check(h.lib.roko_b200_model_set_option(h.ptr, name.encode(), int(value)))
 
     def check_codes(self):
-        """Synchronise and raise IndexError if an earlier forward saw a code outside 0..11."""
+        """Synchronise and raise IndexError if an earlier forward saw a code outside 0..11 (RokoB200Error if a
+        weight or activation left the range of the fp16-split kernels)."""
         for h in self._handles.values():
             _cabi.check(h.lib.roko_b200_model_check(h.ptr))

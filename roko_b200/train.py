@@ -16,9 +16,13 @@ Reference behaviour mirrored (file:line in /root/reference/roko):
     ``rnn_model_<n>_acc=<score>.pth`` holding the state_dict, one file kept             train.py:73-84
 
 ignite, tqdm and torchvision are not needed.  ``h5py`` is needed to read real files (absent in this
-image; tests inject an in-memory stand-in).  Under ``torch.distributed`` (one process per GPU) every
-rank takes its slice of each batch, gradients are averaged with one flat all-reduce
-(``dist.average_gradients``) and rank 0 evaluates and writes checkpoints.
+image; tests inject an in-memory stand-in).  Under ``torch.distributed`` (one process per GPU) ``--b`` is the
+batch PER GPU (BASELINE.json config 5: 128 windows per GPU): the loader yields global batches of
+``b x world`` windows, rank r takes windows [r b, (r+1) b), every rank's loss is the sum over its positions
+divided by the GLOBAL position count, and one flat all-reduce (``dist.sum_gradients``) adds the gradients --
+exactly the gradient of the mean loss over the global batch, also for a ragged last batch or an empty
+shard.  Dropout masks differ per rank (the rank is mixed into the seed); rank 0 evaluates and writes
+checkpoints.
 """
 import argparse
 import os
@@ -241,18 +245,21 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
         shuffle_seed = box[0]
     gen = torch.Generator()
     gen.manual_seed(shuffle_seed)
+    if world > 1:                                                           # shuffles agree across ranks, dropout masks must not
+        torch.manual_seed(shuffle_seed * 1000003 + rank)
+    global_batch = batch_size * world
     pin = torch.cuda.is_available()
     if mem:                                                                 # batch-granular gathers, no per-item collate
         train_dl = val_dl = None                                            # built once the device is known
     else:
-        train_dl = DataLoader(train_ds, batch_size, shuffle=True, num_workers=workers, pin_memory=pin, generator=gen)
+        train_dl = DataLoader(train_ds, global_batch, shuffle=True, num_workers=workers, pin_memory=pin, generator=gen)
         val_dl = DataLoader(val_ds, batch_size, num_workers=workers, pin_memory=pin) if val_ds is not None else None
 
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     device = torch.device(device)
     if mem:
-        train_dl = SlabLoader(train_ds, batch_size, shuffle=True, generator=gen, device=device)
+        train_dl = SlabLoader(train_ds, global_batch, shuffle=True, generator=gen, device=device)
         val_dl = SlabLoader(val_ds, batch_size, device=device) if val_ds is not None else None
     if model is None:
         model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)          # raises without a B200: no CPU path
@@ -267,26 +274,31 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
     running = None                       # ignite's RunningAverage, kept on the device: no host sync per step
     for epoch in range(1, epochs + 1):
         for i, (x, y) in enumerate(train_dl, 1):
-            if world > 1:                                                   # this rank's slice of the batch
-                lo, hi = rdist.shard_range(x.shape[0], rank, world)
+            n_global = x.shape[0]
+            if world > 1:                                                   # this rank's windows of the global batch
+                lo, hi = min(rank * batch_size, n_global), min((rank + 1) * batch_size, n_global)
                 x, y = x[lo:hi], y[lo:hi]
             x = x.to(device, non_blocking=True)
             y = y.to(device, non_blocking=True).long()
             model.train()
             model.zero_grad()
-            loss = F.cross_entropy(model(x).transpose(1, 2), y) if x.shape[0] else None
-            if loss is not None:
+            loss = None
+            if x.shape[0]:
+                # sum over my positions / GLOBAL position count: the all-reduced SUM is the gradient of the global mean
+                loss = F.cross_entropy(model(x).transpose(1, 2), y, reduction="sum") / (n_global * y.shape[1])
                 loss.backward()
             if world > 1:
-                rdist.average_gradients(model)
+                rdist.sum_gradients(model)
             optim.step()
             if loss is not None:
-                v = loss.detach()
+                v = loss.detach() * (n_global / x.shape[0])                 # this rank's mean loss, for the log line
                 running = v.clone() if running is None else running.mul_(RUNNING_ALPHA).add_(v, alpha=1.0 - RUNNING_ALPHA)
             if i % 100 == 0:
                 log(f"ITERATION {i}/{len(train_dl)} - loss: {float(running) if running is not None else None}")
         history["train_loss"].append(float(running) if running is not None else None)
         history["epochs"] = epoch
+        if hasattr(model, "check_codes"):
+            model.check_codes()              # nn.Embedding would have raised IndexError on a code outside 0..11
         if val_dl is None:
             continue
         stop = False

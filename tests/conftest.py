@@ -68,3 +68,27 @@ def train_model(seed1_state):
 def train_golden():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "train_seed1.npz")))
+
+
+@pytest.fixture()
+def make_model(seed1_state):
+    """Factory of fresh inference models on cuda:0 with C-library options applied (kernel A/B selection)."""
+    def make(**options):
+        from roko_b200.rnn_model import RNN, IN_SIZE, HIDDEN_SIZE, NUM_LAYERS
+        m = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS)
+        m.load_state_dict(seed1_state, strict=True)
+        m = m.to("cuda:0").eval().requires_grad_(False)
+        for k, v in options.items():
+            m.set_option(k, v)
+        return m
+    return make
+
+
+@pytest.fixture(scope="session")
+def golden_b128():
+    import numpy as np
+    from roko_b200.synth import structured_windows
+    g = dict(np.load(os.path.join(GOLDEN, "golden_b128_seed1.npz")))
+    g["x"] = structured_windows(128, seed=int(g["seed"]))
+    assert int(g["x"].astype(np.int64).sum()) == int(g["x_crc"])
+    return g

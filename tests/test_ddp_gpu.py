@@ -81,3 +81,50 @@ def test_ddp_and_average_gradients_match_full_batch(seed1_state):
         assert np.abs(g_ddp - full).max() <= 1e-4 * scale, rank
         assert np.abs(g_avg - full).max() <= 1e-4 * scale, rank
     assert np.array_equal(res[0][1], res[1][1])          # DDP leaves identical gradients on both ranks
+
+
+def _infer_worker(rank, world, port, q, n_total):
+    """One rank of sharded inference: contiguous window range, NCCL weight broadcast, label gather to rank 0."""
+    import torch.distributed as dist
+    from roko_b200 import dist as rdist
+    from roko_b200.rnn_model import RNN
+    from roko_b200.synth import structured_windows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        m = RNN(500, 128, 3)
+        if rank == 0:                                   # only rank 0 has the weights; the others get them over NCCL
+            m.load_state_dict(torch.load(os.path.join(root, "tests", "golden", "rand_seed1.pth"), map_location="cpu"))
+        m = m.cuda().eval().requires_grad_(False)
+        rdist.broadcast_weights(m, src=0)
+        x = structured_windows(n_total, seed=4242)
+        lo, hi = rdist.shard_range(n_total, rank, world)
+        local = m.predict(torch.from_numpy(x[lo:hi]).cuda())
+        got = rdist.gather_labels(local, n_total)
+        if rank == 0:
+            q.put(got.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_inference_equals_single_gpu(cuda_model):
+    """shard -> gather equals the single-GPU output byte for byte (ragged shards: 301 windows)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from roko_b200.synth import structured_windows
+    n_total = 301
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_infer_worker, args=(r, 2, port, q, n_total)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = cuda_model.predict(torch.from_numpy(structured_windows(n_total, seed=4242)).cuda()).cpu().numpy()
+    assert got.shape == single.shape and np.array_equal(got, single)

@@ -99,13 +99,14 @@ def _train_worker(rank, world, port, outdir, q):
         ok_avg = bool(torch.allclose(m.fc.weight.grad, torch.full_like(m.fc.weight, 1.5))
                       and torch.allclose(m.fc.bias.grad, torch.full_like(m.fc.bias, 2.0)))
 
-        # (2) two ranks training on halves of every batch == one process training on whole batches
-        x, y = structured_windows(32, seed=21, return_truth=True)
-        pos = np.zeros((32, 90, 2), np.int64)
+        # (2) two ranks with 4 windows per rank and step == one process with 8 windows per step, including the ragged
+        # last batch of 30 windows (6 = 4 + 2: shards weigh in by their size, not as a mean of means)
+        x, y = structured_windows(30, seed=21, return_truth=True)
+        pos = np.zeros((30, 90, 2), np.int64)
         fake_h5.register("mem://dist_train", {"c": "ACGT"}, [("c_0", "c", pos, x, y)])
         torch.manual_seed(100 + rank)                     # different initial weights: rank 0's must win
         model = TinyModel()
-        hist = T.train("mem://dist_train", outdir, "mem://dist_train", mem=True, batch_size=8, epochs=2, lr=1e-2,
+        hist = T.train("mem://dist_train", outdir, "mem://dist_train", mem=True, batch_size=4, epochs=2, lr=1e-2,
                        model=model, device="cpu", h5=fake_h5, log=lambda *_: None, seed=5)
         flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
         q.put((rank, ok_avg, nbytes, flat.numpy(), hist["checkpoint"]))
@@ -128,13 +129,13 @@ def test_data_parallel_training_world2(tmp_path):
     assert np.allclose(res[0][3], res[1][3], atol=1e-7)          # ranks stay in lock step
     assert res[0][4] is not None and res[1][4] is None            # rank 0 alone writes checkpoints
 
-    # single-process run from rank 0's start: mean of the two half-batch gradients == whole-batch gradient
+    # single-process run from rank 0's start with the global batch (8): size-weighted shard gradients == whole-batch gradient
     from roko_b200 import train as T
     from roko_b200.synth import structured_windows
     from tests import fake_h5
     from tests.test_train_host import TinyModel
-    x, y = structured_windows(32, seed=21, return_truth=True)
-    fake_h5.register("mem://dist_train", {"c": "ACGT"}, [("c_0", "c", np.zeros((32, 90, 2), np.int64), x, y)])
+    x, y = structured_windows(30, seed=21, return_truth=True)
+    fake_h5.register("mem://dist_train", {"c": "ACGT"}, [("c_0", "c", np.zeros((30, 90, 2), np.int64), x, y)])
     torch.manual_seed(100)
     model = TinyModel()
     T.train("mem://dist_train", str(tmp_path / "single"), None, mem=True, batch_size=8, epochs=2, lr=1e-2,

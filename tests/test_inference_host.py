@@ -83,6 +83,52 @@ def test_dense_vote_table_matches_counter_semantics(seed):
     assert [("ctgA", inf.stitch(contigs["ctgA"], p, w))] == reference_vote_and_stitch(contigs, batches)
 
 
+@pytest.mark.parametrize("budget,reverse", [(4 << 30, False), (4 << 30, True), (20_000, False), (0, True)])
+def test_dense_vote_table_grows_spills_and_releases(budget, reverse):
+    """Tables are sized from the positions seen (growing in either direction), fall back to the sparse table over
+    budget (mid-contig too), and are freed per contig -- with Counter semantics intact throughout."""
+    import torch
+    rng = np.random.default_rng(7)
+    contigs = {"ctgA": "".join(rng.choice(list("ACGT"), 900)), "ctgB": "".join(rng.choice(list("ACGT"), 300))}
+    votes, batches = inf.DenseVoteTable("cpu", budget_bytes=budget), []
+    for name in contigs:
+        pos = make_windows(rng, len(contigs[name]), 25)
+        Y = rng.integers(0, 5, size=pos.shape[:2]).astype(np.uint8)
+        starts = list(range(0, len(pos), 4))
+        for b0 in (reversed(starts) if reverse else starts):
+            sl = slice(b0, b0 + 4)
+            batches.append(([name] * len(pos[sl]), pos[sl], Y[sl]))
+            votes.add(name, 10, torch.from_numpy(pos[sl].reshape(-1, 2)), torch.from_numpy(Y[sl].reshape(-1)))   # wrong attrs['len'] is harmless
+    assert votes.contigs() == ["ctgA", "ctgB"]
+    mine = []
+    for contig in votes.contigs():
+        p, w = votes.consensus(contig)
+        mine.append((contig, inf.stitch(contigs[contig], p, w)))
+        votes.release(contig)
+    assert mine == reference_vote_and_stitch(contigs, batches)
+    assert not votes.tables and not votes.sparse.tables
+    with pytest.raises(IndexError):
+        votes.add("ctgA", 900, torch.tensor([[5, 4]]), torch.tensor([1], dtype=torch.uint8))      # ins > MAX_INS
+
+
+def test_slab_dataset_shards_cover_the_file_once():
+    rng = np.random.default_rng(5)
+    ex = rng.integers(0, 12, (11, 200, 90), dtype=np.uint8)
+    pos = rng.integers(0, 50, (11, 90, 2)).astype(np.int64)
+    fake_h5.register("mem://shard", {"c": "ACGT" * 50}, [("g0", "c", pos[:4], ex[:4]), ("g1", "c", pos[4:9], ex[4:9]), ("g2", "c", pos[9:], ex[9:])])
+    from roko_b200.dist import shard_range
+    for world in (1, 2, 3, 4):
+        seen = []
+        for r in range(world):
+            lo, hi = shard_range(11, r, world)
+            ds = inf._SlabDataset("mem://shard", 3, h5=fake_h5, lo=lo, hi=hi)
+            for i in range(len(ds)):
+                c, p, x, flat = ds[i]
+                assert np.array_equal(x.numpy(), ex[flat:flat + len(x)]) and np.array_equal(p.numpy(), pos[flat:flat + len(x)])
+                seen.extend(range(flat, flat + len(x)))
+        assert seen == list(range(11))
+
+
 def test_fasta_writer_format(tmp_path):
     path = tmp_path / "o.fasta"
     inf.write_fasta([("c1", "A" * 130), ("c2", "ACGT")], str(path))

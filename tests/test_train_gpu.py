@@ -67,6 +67,34 @@ def test_gradients_match_reference_fixture(train_model, train_golden):
         assert abs(flat.sum() - float(g[f"sum/{k}"])) <= GRAD_TOL * norm * np.sqrt(flat.size), k
 
 
+def test_gradients_at_batch_128_match_reference_fixture(train_model):
+    """The timed training shape (BASELINE.json config 5: 128 windows per GPU): the streamed tcgen05 products split
+    576 000 rows over 148 CTAs and the generic GEMM accumulates with atomics -- all of that against gradients of
+    the reference class itself (tests/golden/train_b128_seed1.npz).  Tolerance 1e-3 of each tensor's max, not 1e-4:
+    among 57 M ReLU pre-activations some lie within fp32 noise of 0, where any two fp32 implementations pick
+    different sides of the kink (the reference in fp32 vs fp64 does too); each such flip moves a few entries."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "train_b128_seed1.npz")))
+    x, y = structured_windows(128, seed=int(g["seed"]), return_truth=True)
+    train_model.eval()
+    logits, loss = _loss(train_model, x, y)
+    loss.backward()
+    assert np.abs(logits.detach().cpu().numpy()[:4] - g["logits4"]).max() <= LOGIT_TOL
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5
+    got = _grads(train_model)
+    worst = ("", 0.0)
+    for k in TO.STATE_KEYS:
+        flat = got[k].reshape(-1)
+        assert np.isfinite(flat).all(), k
+        ref = g[f"sample/{k}"].astype(np.float64)
+        err = np.abs(flat[TO.sample_index(flat.size)] - ref).max() / (np.abs(ref).max() + 1e-30)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        assert err <= 1e-3, (k, err)
+        norm = float(g[f"norm/{k}"])
+        assert abs(np.sqrt((flat * flat).sum()) - norm) / norm <= 1e-3, k
+    print("batch-128 worst relative gradient error", worst)
+
+
 @pytest.mark.parametrize("batch", [1, 2, 5])
 def test_gradients_match_oracle_no_dropout(train_model, seed1_weights, batch):
     x, y = structured_windows(batch, seed=CLEAR_SEEDS[batch], return_truth=True)

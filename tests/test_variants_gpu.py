@@ -28,8 +28,8 @@ assert err <= 5e-6 and same
 
 
 @pytest.mark.parametrize("env", [
-    {"ROKO_B200_PROJ": "tc1"}, {"ROKO_B200_PROJ": "tc1", "ROKO_B200_PROJ_CLUSTER": "2"}, {"ROKO_B200_PROJ": "tc2"},
-    {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_REC_TC_MIN": "0"}, {"ROKO_B200_REC_NB": "4"},
+    {"ROKO_B200_PROJ": "tf32"}, {"ROKO_B200_REC": "tf32"}, {"ROKO_B200_PROJ": "tf32", "ROKO_B200_REC": "tf32"},
+    {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_REC_TC_MIN": "0"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_GRAPHS": "0"},
 ], ids=lambda e: ",".join(f"{k.replace('ROKO_B200_', '')}={v}" for k, v in e.items()))
 def test_kernel_variant(env):
     p = subprocess.run([sys.executable, "-c", CHECK], env={**os.environ, **env}, capture_output=True, text=True, timeout=180)
@@ -61,7 +61,7 @@ print("OK")
 
 
 @pytest.mark.parametrize("env", [
-    {"ROKO_B200_REC_NB": "2"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_PROJ": "ffma"},
+    {"ROKO_B200_REC_NB": "2"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_PROJ": "tf32"},
     {"ROKO_B200_TRAIN_TC": "4"}, {"ROKO_B200_TRAIN_TC": "2"}, {"ROKO_B200_TRAIN_TC": "1"}, {"ROKO_B200_TRAIN_TC": "0"}, {"ROKO_B200_TRAIN_TC": "0", "ROKO_B200_GEMM_NOSTREAM": "1"},
 ], ids=lambda e: ",".join(f"{k.replace('ROKO_B200_', '')}={v}" for k, v in e.items()))
 def test_training_kernel_variant(env):

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libroko_b200.so")
 OBJ = os.path.join(CSRC, "build")
-SOURCES = ["pack.cu", "front.cu", "proj.cu", "proj_tc3.cu", "proj_h.cu", "rec.cu", "rec_tc.cu", "rec_h.cu", "head.cu", "api.cu",
+SOURCES = ["pack.cu", "front.cu", "front_tc.cu", "proj.cu", "proj_tc3.cu", "proj_h.cu", "rec.cu", "rec_tc.cu", "rec_h.cu", "head.cu", "api.cu",
            "gemm.cu", "train.cu", "train_tc.cu", "rec_bwd.cu", "train_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -76,7 +76,8 @@ int run_forward(roko_b200_model* m, const uint8_t* x, int n, float* logits, uint
         const int nc = (n - c0) < cap ? (n - c0) : cap;
         const int rows = nc * COLS;
         if (ev) CU(cudaEventRecord(ev[0], s));
-        CU(launch_front(x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
+        if (m->front_kind == 1) CU(launch_front_tc(x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
+        else CU(launch_front(x + (size_t)c0 * WIN_BYTES, pk, u, nc, m->status, m->num_sms, s));
         if (taps && taps->front)
             CU(cudaMemcpy2DAsync(taps->front, IN0 * sizeof(float), u, IN0P * sizeof(float), IN0 * sizeof(float),
                                  rows, cudaMemcpyDeviceToDevice, s));
@@ -252,6 +253,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = cudaMalloc(&m->status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->status, 0, sizeof(int));
     if (e == cudaSuccess) e = front_setup();
+    if (e == cudaSuccess) e = front_tc_setup();
     if (e == cudaSuccess) e = rec_setup();
     if (e == cudaSuccess) e = proj_tc3_setup();
     if (e == cudaSuccess) e = proj_h_setup();
@@ -262,6 +264,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (const char* pj = getenv("ROKO_B200_PROJ")) m->use_tc = strcmp(pj, "ffma") == 0 ? 0 : (strcmp(pj, "tf32") == 0 ? 3 : 4);
     if (const char* rk = getenv("ROKO_B200_REC")) m->rec_kind = strcmp(rk, "tf32") == 0 ? 1 : 2;
     if (const char* gr = getenv("ROKO_B200_GRAPHS")) m->use_graphs = atoi(gr);
+    if (const char* fr = getenv("ROKO_B200_FRONT")) m->front_kind = strcmp(fr, "tc") == 0 ? 1 : 0;
     if (e != cudaSuccess) {
         roko_b200_model_destroy(m);
         return fail(ROKO_B200_ECUDA, "model_create: %s%s", cudaGetErrorString(e));

@@ -100,7 +100,8 @@ constexpr int RTC_DIR = 2 * RTC_W + HID;         // floats per direction
 __host__ __device__ constexpr int pk_rtc(int l, int d) { return pk_wtc(LAYERS) + (l * 2 + d) * RTC_DIR; }
 // fp16-split operands (tc.cuh) -- the default kernels:
 //   WH16 (proj_h.cu)  W_ih x 256 as fp16 hi / lo shared-memory images  [n_tile 3][k block of 64][hi|lo][256 rows x 128 B, SWIZZLE_128B]
-//   RH16 (rec_h.cu)   W_hh x 256 as fp16 hi / lo tensor-memory images  [gate tile 3][hi|lo][row 128][64 words: k = 2c, 2c+1], then b_hn[128]
+//   RH16 (rec_h.cu)   W_hh x 256: hi halves as a tensor-memory image [gate tile 3][row 128][64 words: k = 2c, 2c+1], lo halves as a
+//                     shared-memory image [gate tile 3][k atom 2][128 rows x 128 B, SWIZZLE_128B], then b_hn[128]
 constexpr int H16_BK = 64;                       // fp16 elements per k block (one 128-byte swizzle row)
 constexpr int H16_IMG = TC_BN * H16_BK / 2;      // floats in one hi (or lo) image of 256 rows: 32 KB
 __host__ __device__ constexpr int pk_wh16_size(int l) { return (GI_N / TC_BN) * (gru_inp(l) / H16_BK) * 2 * H16_IMG; }
@@ -112,7 +113,18 @@ __host__ __device__ constexpr int pk_wh16(int l) {
 constexpr int RH16_W = 3 * 2 * HID * (HID / 2);  // 49 152 words
 constexpr int RH16_DIR = RH16_W + HID;
 __host__ __device__ constexpr int pk_rh16(int l, int d) { return pk_wh16(LAYERS) + (l * 2 + d) * RH16_DIR; }
-constexpr int PK_TOTAL = pk_rh16(LAYERS, 0);
+// fp16-split operands of the tcgen05 front end (front_tc.cu); scales: W1, E, M x 16; a, W2 x 256
+//   FT_W1HI  [128 rows j][104 words: r = 2c, 2c+1]   W1[j][r] x 16, hi halves -- tensor-memory image (rows >= 100 zero)
+//   FT_W1LO  [7 k atoms of 32 r][128 rows j][64 B]   lo halves, K-major SWIZZLE_64B shared-memory image (r < 208 used)
+//   FT_W2    [2 k atoms of 64 j][32 rows: hi of k = row, lo of k = row - 16][128 B]   W2[k][j] x 256, column j = 100 holds b2[k] x 256, SWIZZLE_128B
+constexpr int FT_K1 = 208;                       // read axis padded to 13 k steps of 16
+constexpr int FT_W1HI_WORDS = 128 * (FT_K1 / 2);
+constexpr int FT_W1LO_WORDS = 7 * 128 * 16;
+constexpr int FT_W2_WORDS = 2 * 2 * 16 * 32;
+constexpr int PK_FT_W1HI = pk_rh16(LAYERS, 0);
+constexpr int PK_FT_W1LO = PK_FT_W1HI + FT_W1HI_WORDS;
+constexpr int PK_FT_W2 = PK_FT_W1LO + FT_W1LO_WORDS;
+constexpr int PK_TOTAL = PK_FT_W2 + FT_W2_WORDS;
 
 // ---- workspace per window (floats) ------------------------------------------------------------
 constexpr size_t WS_U = (size_t)COLS * IN0P;     // front-end output, k-padded
@@ -146,6 +158,9 @@ cudaError_t launch_head(const float* h, const float* w4, const float* b4, float*
                         int rows, cudaStream_t s);
 cudaError_t measure_fp32_peak(double* tflops);
 cudaError_t front_setup();
+cudaError_t launch_front_tc(const uint8_t* x, const float* packed, float* u, int nwin, int* status, int num_sms,
+                            cudaStream_t s);
+cudaError_t front_tc_setup();
 cudaError_t rec_setup();
 
 }  // namespace roko

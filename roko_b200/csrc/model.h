@@ -59,7 +59,8 @@ struct roko_b200_model {
     std::mutex mu;
     unsigned long long graph_clock = 0;
     int use_graphs = 1;             // replay the chain as a CUDA graph when the batch fits the workspace (ROKO_B200_GRAPHS=0 disables)
-    int front_kind = 0;             // front end: 0 = warp-level mma.sync stages (front.cu); 1 = tcgen05 stages (front_tc.cu)
+    int front_kind = 1;             // front end: 1 = all three contractions on tcgen05 (front_tc.cu, default); 0 = SIMT gather + warp-level
+                                    // mma.sync stages (front.cu, round 1).  ROKO_B200_FRONT=tc|mma
 };
 
 // offset of raw element `off` inside raw_al (RAW_GRU is 2 mod 4 and every later tensor size is a multiple of 4)

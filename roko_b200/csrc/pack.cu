@@ -59,17 +59,61 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p, 
             const __half b = lo ? __float2half_rn(v1 - __half2float(h1)) : h1;
             return __uint_as_float((uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16));
         };
-        if (p >= pk_rh16(0, 0)) {                      // rec_h.cu: W_hh [gate tile][hi|lo][row][word c: k = 2c, 2c+1], b_hn
+        if (p >= PK_FT_W1HI) {                         // front_tc.cu operands (scales: W1 x 16, W2 x 256)
+            auto pair_s = [&](float v0, float v1, float scale, bool lo) -> float {
+                v0 *= scale; v1 *= scale;
+                if (fabsf(v0) > 65000.f || fabsf(v1) > 65000.f) atomicOr(status, 2);
+                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                const __half a = lo ? __float2half_rn(v0 - __half2float(h0)) : h0;
+                const __half b = lo ? __float2half_rn(v1 - __half2float(h1)) : h1;
+                return __uint_as_float((uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16));
+            };
+            auto w1 = [&](int j, int r) { return (j < FC1 && r < READS) ? raw[RAW_W1 + j * READS + r] : 0.f; };
+            if (p < PK_FT_W1LO) {                      // [j][word c]: r = 2c, 2c+1, hi halves
+                const int i = p - PK_FT_W1HI, j = i / (FT_K1 / 2), c = i % (FT_K1 / 2);
+                return pair_s(w1(j, 2 * c), w1(j, 2 * c + 1), 16.f, false);
+            }
+            if (p < PK_FT_W2) {                        // [k atom][row j][64 B], SWIZZLE_64B: chunk position = chunk ^ ((row >> 1) & 3)
+                const int ob = (p - PK_FT_W1LO) * 4;
+                const int atom = ob / (128 * 64), within = ob % (128 * 64);
+                const int j = (within / 512) * 8 + (within % 512) / 64;
+                const int pchunk = (within % 64) / 16, w4 = (within % 16) / 4;
+                const int r = atom * 32 + ((pchunk ^ ((j >> 1) & 3)) * 8) + w4 * 2;
+                return pair_s(w1(j, r), w1(j, r + 1), 16.f, true);
+            }
+            {                                          // W2: [k atom of 64 j][32 rows: hi of k = row (0..15), lo of k = row - 16][128 B], SWIZZLE_128B; j = 100 carries b2
+                const int ob = (p - PK_FT_W2) * 4;
+                const int atom = ob / (32 * 128), within = ob % (32 * 128);
+                const int row = (within / 1024) * 8 + (within % 1024) / 128;
+                const int pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+                const int j = atom * 64 + ((pchunk ^ (row & 7)) * 8) + w4 * 2;
+                const int k = row & 15;
+                auto w2 = [&](int kk, int jj) {
+                    if (kk >= FC2) return 0.f;
+                    if (jj < FC1) return raw[RAW_W2 + kk * FC1 + jj];
+                    return jj == FC1 ? raw[RAW_B2 + kk] : 0.f;
+                };
+                return pair_s(w2(k, j), w2(k, j + 1), 256.f, row >= 16);
+            }
+        }
+        if (p >= pk_rh16(0, 0)) {                      // rec_h.cu: W_hh hi (tensor-memory rows), lo (swizzled shared-memory image), b_hn
             int i = p - pk_rh16(0, 0);
             const int ld = i / RH16_DIR, l = ld / 2, d = ld % 2;
             i %= RH16_DIR;
             if (i >= RH16_W) return raw[raw_bhh(l, d) + 2 * HID + (i - RH16_W)];
-            const int mt = i / (2 * HID * (HID / 2));
-            i %= 2 * HID * (HID / 2);
-            const bool lo = i >= HID * (HID / 2);
+            const bool lo = i >= RH16_W / 2;
+            i %= RH16_W / 2;
+            const int mt = i / (HID * (HID / 2));
             i %= HID * (HID / 2);
-            const int row = i / (HID / 2), c = i % (HID / 2);
-            const float* w = raw + raw_whh(l, d) + (mt * HID + row) * HID + 2 * c;
+            int row, k;
+            if (!lo) { row = i / (HID / 2); k = 2 * (i % (HID / 2)); }
+            else {
+                const int ob = i * 4, katom = ob / 16384, within = ob % 16384;
+                row = (within / 1024) * 8 + (within % 1024) / 128;
+                const int pchunk = (within % 128) / 16, w4 = (within % 16) / 4;
+                k = katom * 64 + ((pchunk ^ (row & 7)) * 8) + w4 * 2;
+            }
+            const float* w = raw + raw_whh(l, d) + (mt * HID + row) * HID + k;
             return pair(w[0], w[1], lo);
         }
         int l = 0;                                     // proj_h.cu: W_ih images, 128-byte swizzle, 64-element k blocks

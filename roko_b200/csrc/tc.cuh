@@ -146,13 +146,14 @@ __device__ __forceinline__ void split_f16(float v, unsigned short& hi, unsigned 
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(l);
 }
-// two values -> packed hi word (v0 in the low half) and packed lo word
+// two values -> packed hi word (v0 in the low half) and packed lo word: one packed convert, two unpacks, two
+// subtractions, one packed convert (6 instructions for two values)
 __device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    unsigned short h0, l0, h1, l1;
-    split_f16(v0, h0, l0);
-    split_f16(v1, h1, l1);
-    hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
-    lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ float ex2f(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }

@@ -118,7 +118,7 @@ def test_cpu_tensor_fails_loudly(cuda_model, golden):
 
 
 # ---- the batch shapes of BASELINE.json configs 2-4 and the tensor-core kernels at those shapes -------------
-FFMA = dict(proj=0, rec_tc_min=0)          # fp32-exact A/B configuration: FFMA projection + register-resident FFMA recurrence
+FFMA = dict(proj=0, rec_tc_min=0, front=0)     # fp32 A/B configuration: FFMA projection + register-resident FFMA recurrence + round-1 front end
 
 
 def _oracle_subset(logits, labels, x, weights, idx):
@@ -139,7 +139,7 @@ def _subset(n, k=48, seed=0):
     return np.asarray(idx)
 
 
-@pytest.mark.parametrize("opts", [{}, dict(proj=3, rec=1)], ids=["fp16", "tf32"])
+@pytest.mark.parametrize("opts", [{}, dict(proj=3, rec=1, front=0)], ids=["fp16", "round1-tf32"])
 def test_tensor_core_recurrence_at_batch_128(make_model, golden_b128, opts):
     """The exact shape bench.py times: one 128-window batch, recurrence on tcgen05 (4 CTAs per direction)."""
     m = make_model(rec_tc_min=64, **opts)

@@ -29,7 +29,7 @@ assert err <= 5e-6 and same
 
 @pytest.mark.parametrize("env", [
     {"ROKO_B200_PROJ": "tf32"}, {"ROKO_B200_REC": "tf32"}, {"ROKO_B200_PROJ": "tf32", "ROKO_B200_REC": "tf32"},
-    {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_REC_TC_MIN": "0"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_GRAPHS": "0"},
+    {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_REC_TC_MIN": "0"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_GRAPHS": "0"}, {"ROKO_B200_FRONT": "mma"},
 ], ids=lambda e: ",".join(f"{k.replace('ROKO_B200_', '')}={v}" for k, v in e.items()))
 def test_kernel_variant(env):
     p = subprocess.run([sys.executable, "-c", CHECK], env={**os.environ, **env}, capture_output=True, text=True, timeout=180)

@@ -50,9 +50,12 @@ size_t roko_b200_workspace_bytes(int max_windows);
 /* RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)        -- roko/inference.py:94, rnn_model.py:25-44 */
 int roko_b200_model_create(roko_b200_model** out, int device);
 /* model.load_state_dict(torch.load(path))                 -- roko/inference.py:95
- * `raw` holds the 31 tensors flattened in state_dict order, host or device
- * memory.  Repacks them into the kernels' layouts; call again whenever the parameters change.
- * Synchronises `stream` (it reads back the 87 KB the front-end kernel takes as parameters). */
+ * `raw` holds the 31 tensors flattened in state_dict order; `raw_on_device` bit 0 says
+ * whether that is device (1) or host (0) memory.  Repacks them into the kernels' layouts (fp32 tables, fp16
+ * hi/lo operand images for the tensor-core kernels); call again whenever the parameters change.
+ * Synchronises `stream` before returning unless bit 1 of `raw_on_device` is set (2 | on_device): every kernel
+ * reads its weights from the packed buffer, so later work on the SAME stream is ordered without a host
+ * synchronisation (the training path reloads every step this way). */
 int roko_b200_model_load(roko_b200_model* m, const float* raw, int raw_on_device, void* stream);
 int roko_b200_model_destroy(roko_b200_model* m);
 
@@ -74,17 +77,24 @@ int roko_b200_forward_i64(roko_b200_model* m, const int64_t* x, int n_windows, f
 int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_windows, int batch,
                          uint8_t* labels_host, float* logits_host);
 
-/* Scheduling knobs (no effect on results beyond fp32 rounding order):
- *   "rec_tc_min"  chunks of at least this many windows run the recurrence on tcgen05 (default 256; 0 = never).
- *                 Below it the register-resident FFMA recurrence has the lower latency; the tensor-core
- *                 recurrence occupies 1/16 of the SMs per 128 windows and wins when several batches are in
- *                 flight on different streams.
- *   "superbatch"  windows per device pass of roko_b200_infer_host (default 2368)
- *   "proj"        projection kernel: 3 persistent tcgen05 (default), 2 / 1 other tile shapes, 0 FFMA SGEMM */
+/* Scheduling and kernel-selection knobs (no effect on results beyond fp32 rounding order; every setting passes the
+ * same parity tests):
+ *   "rec_tc_min"    chunks of at least this many windows run the recurrence on tcgen05 (default 64; 0 = never).  Below it
+ *                   the register-resident FFMA recurrence spreads few windows over many SMs for the lowest latency.
+ *   "rec"           tensor-core recurrence kernel: 2 fp16-split, 48 MMAs per step (rec_h.cu, default); 1 3xTF32 (rec_tc.cu)
+ *   "rec_pingpong"  rec_h.cu: two 32-window groups per CTA one step out of phase: 0 never, 1 when a pass holds more groups
+ *                   than CTA pairs (default), 2 always
+ *   "proj"          projection kernel: 4 tcgen05 fp16-split (proj_h.cu, default), 3 tcgen05 3xTF32, 0 FFMA SGEMM
+ *   "front"         front end: 1 all contractions on tcgen05 (front_tc.cu, default), 0 SIMT gather + mma.sync (front.cu)
+ *   "graphs"        replay the 8-kernel chain of roko_b200_forward_u8 as a CUDA graph (default 1; needs a non-default stream)
+ *   "superbatch"    windows per device pass of roko_b200_infer_host (default 2368)
+ * The fp16-split kernels scale their operands by powers of two (weights x 256, activations x 16 / x 256); a GRU weight
+ * with |w| >= 253 or a front-end activation >= 4062 leaves their range: roko_b200_model_check then returns
+ * ROKO_B200_ERANGE and the tf32 kernels ("proj" 3, "rec" 1) serve such a model. */
 int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long value);
 
-/* Synchronises the device and reports sticky input errors seen by earlier forwards
- * (bit 0: code outside 0..11), then clears them.  Returns ROKO_B200_ECODES if any were set. */
+/* Synchronises the device and reports sticky errors seen by earlier calls, then clears them: ROKO_B200_ECODES for an
+ * input code outside 0..11, ROKO_B200_ERANGE for a weight / activation outside the fp16-split range (see above). */
 int roko_b200_model_check(roko_b200_model* m);
 
 /* Stage taps for parity tests: run the path over n_windows (<= what fits the workspace) and copy

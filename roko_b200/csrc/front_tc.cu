@@ -80,7 +80,7 @@ __host__ __device__ constexpr uint32_t sw64_off(uint32_t row, uint32_t chunk) {
 
 // relu(D2) -> fp16 hi / lo words for two adjacent j (D2 is already 256 a: scales 16 x 16)
 __device__ __forceinline__ void relu_split2(uint32_t d0, uint32_t d1, uint32_t& hi, uint32_t& lo) {
-    split_f16x2(fmaxf(__uint_as_float(d0), 0.f), fmaxf(__uint_as_float(d1), 0.f), hi, lo);
+    relu_split_f16x2(__uint_as_float(d0), __uint_as_float(d1), hi, lo);
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -314,25 +314,31 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
             for (int h = 0; h < FT_GROUPS; ++h) {
                 const uint32_t hg = (uint32_t)it * FT_GROUPS + h, hb = hg & 1;
                 const int p = 4 * h + pl;
-                uint32_t code[8];
+                uint32_t c03 = 0xFFFFFFFFu, c47 = 0xFFFFFFFFu;           // my 8 codes, one per byte (0xFF = no read)
                 if (t < 104 && p < COLS) {
+                    uint32_t code[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 8 * rc + i;
                         code[i] = r < READS ? xs[r * COLS + p] : 255u;
                         bad |= (r < READS && code[i] >= NCODES);
                     }
+                    c03 = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+                    c47 = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
                 }
                 mbar_wait(BAR(B_OHEMPTY + hb), ((hg >> 1) & 1) ^ 1);     // MMA1 of group hg - 2 has consumed this buffer
                 if (t < 104 && p < COLS) {
                     unsigned char* oh = smem + FT_S_OH + hb * FT_OH_BYTES;
 #pragma unroll
                     for (int c = 0; c < NCODES; ++c) {
-                        uint4 o;                                         // fp16 1.0 = 0x3C00 where the read carries code c
-                        o.x = (code[0] == (uint32_t)c ? 0x3C00u : 0u) | (code[1] == (uint32_t)c ? 0x3C000000u : 0u);
-                        o.y = (code[2] == (uint32_t)c ? 0x3C00u : 0u) | (code[3] == (uint32_t)c ? 0x3C000000u : 0u);
-                        o.z = (code[4] == (uint32_t)c ? 0x3C00u : 0u) | (code[5] == (uint32_t)c ? 0x3C000000u : 0u);
-                        o.w = (code[6] == (uint32_t)c ? 0x3C00u : 0u) | (code[7] == (uint32_t)c ? 0x3C000000u : 0u);
+                        // byte-wise compare (0xFF where the read carries code c), bytes spread to the high byte of each half,
+                        // masked to fp16 1.0 = 0x3C00
+                        const uint32_t m0 = __vcmpeq4(c03, 0x01010101u * (uint32_t)c), m1 = __vcmpeq4(c47, 0x01010101u * (uint32_t)c);
+                        uint4 o;
+                        o.x = __byte_perm(m0, 0u, 0x1404) & 0x3C003C00u;
+                        o.y = __byte_perm(m0, 0u, 0x3424) & 0x3C003C00u;
+                        o.z = __byte_perm(m1, 0u, 0x1404) & 0x3C003C00u;
+                        o.w = __byte_perm(m1, 0u, 0x3424) & 0x3C003C00u;
                         *reinterpret_cast<uint4*>(oh + doff[c]) = o;
                     }
                 }

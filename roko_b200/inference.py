@@ -139,15 +139,19 @@ class VoteTable:
         return np.stack([keys // (MAX_INS + 1), keys % (MAX_INS + 1)], axis=1), winner
 
 
+_DECODE_LUT = np.frombuffer(ALPHABET.encode(), dtype="S1")
+
+
 def stitch(contig_seq, positions, winners):
-    """inference.py:129-147 for one contig: positions sorted [(rpos, ins)], winners label ids."""
+    """inference.py:129-147 for one contig: positions sorted [(rpos, ins)], winners label ids.
+    Vectorised (a byte look-up and a mask instead of a Python loop per base: a 5 Mbp contig stitches in milliseconds)."""
     keep = np.flatnonzero(positions[:, 1] == 0)
     if keep.size == 0:
         raise IndexError("no reference-anchored position for contig")     # the reference raises here too (pos_sorted[0])
     start = keep[0]                                                       # dropwhile(ins != 0)
-    positions, winners = positions[start:], winners[start:]
+    positions, winners = positions[start:], np.asarray(winners[start:], dtype=np.int64)
     first, last = int(positions[0, 0]), int(positions[-1, 0])
-    body = "".join(decoding[int(w)] for w in winners if decoding[int(w)] != GAP)
+    body = _DECODE_LUT[winners[winners != encoding[GAP]]].tobytes().decode("ascii")
     return contig_seq[:first] + body + contig_seq[last + 1:]
 
 
@@ -351,14 +355,23 @@ def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device=None, chunk=8192, vote_budget=4 << 30):
+def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device=None, chunk=8192, vote_budget=4 << 30,
+               stats=None):
     """Throughput driver: slab reads -> predict_host (coalesced device passes) -> dense GPU vote -> stitch.
 
     Launched under ``torchrun`` (WORLD_SIZE > 1, one process per GPU) it shards the flat window range into contiguous
     per-rank ranges, broadcasts the weights from rank 0 over NCCL (one flat 4.4 MB broadcast instead of the
     reference's dormant per-forward ``nn.DataParallel`` replication, roko/inference.py:12,96-97), gathers the uint8
     labels (90 B / window) to rank 0 over NVLink, and rank 0 votes, stitches and writes the FASTA.  Returns the
-    records on rank 0 and ``None`` elsewhere."""
+    records on rank 0 and ``None`` elsewhere.  ``stats`` (a dict) receives wall-clock seconds per phase."""
+    import time
+    clock, t_last = {}, [time.perf_counter()]
+
+    def lap(name):
+        now = time.perf_counter()
+        clock[name] = clock.get(name, 0.0) + now - t_last[0]
+        t_last[0] = now
+
     if not torch.cuda.is_available():
         raise RuntimeError("roko_b200.inference needs a CUDA (sm_100a) device: the model path has no CPU fallback")
     rank, local_rank, world = _dist_env()
@@ -377,6 +390,7 @@ def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device
     if world > 1:
         rdist.broadcast_weights(model, src=0)
     model.eval()
+    lap("setup (process group, model, weights)")
 
     meta = _SlabDataset(data, chunk, h5=h5, examples=False)                # full index (positions only)
     lo, hi = (0, meta.total) if world == 1 else rdist.shard_range(meta.total, rank, world)
@@ -406,28 +420,39 @@ def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device
         print("Inference started")
     local = torch.empty((hi - lo, 90), dtype=torch.uint8, device=device) if world > 1 else None
     done = 0
+    lap("index")
     for contig, pos, x, flat in loader:
         n = x.shape[0]
         x_pin[:n].copy_(x)
+        lap("read + stage")
         model.predict_host(x_pin[:n], batch=batch_size, out=y_pin[:n], device=device)
+        lap("model path (H2D, kernels, D2H)")
         if world > 1:
             local[flat - lo:flat - lo + n].copy_(y_pin[:n])
         else:
             vote(contig, pos, y_pin[:n])
+            lap("vote + stitch")
         done += n
         if rank == 0 and (done // batch_size) % 100 == 0:
             print(f"{done // batch_size} batches processed")
     model.check_codes()                                                   # nn.Embedding would have raised on a bad code
     if world > 1:
         labels = rdist.gather_labels(local, meta.total)                   # (N, 90) uint8 on rank 0, rank order = file order
+        torch.cuda.synchronize(device)
+        lap("label gather (NCCL)")
         if rank != 0:
+            if stats is not None:
+                stats.update(clock)
             return None
-        labels = labels.cpu()
         for i in range(len(meta)):
             contig, pos, _, flat = meta[i]
-            vote(contig, pos, labels[flat:flat + pos.shape[0]])
+            vote(contig, pos, labels[flat:flat + pos.shape[0]])         # labels stay on the GPU: the vote tables live there
+        lap("vote + stitch")
     out_records = [(c, records[c]) for c in order]
     write_fasta(out_records, out)
+    lap("fasta")
+    if stats is not None:
+        stats.update(clock)
     return out_records
 
 

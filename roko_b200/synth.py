@@ -34,3 +34,102 @@ def structured_windows(n, seed=101, return_truth=False):
     x = x + (6 * strand).astype(np.uint8)
     x = np.ascontiguousarray(x, dtype=np.uint8)
     return (x, truth[:, 0, :].copy()) if return_truth else x
+
+
+# ---- synthetic feature FILE: an h5py-like stand-in for BASELINE.json configs 3-5 ---------------------------
+# ``File("synthetic://<n_windows>[?contig_len=..&group=..&seed=..]")`` exposes the roko feature-file schema
+# (SURVEY.md App. C / reference roko/data.py:40-48): one group per region with ``attrs['contig'|'size']``,
+# ``positions`` (n, 90, 2) int64 and ``examples`` (n, 200, 90) uint8, plus ``/contigs/<name>`` with the draft.
+# Windows are generated on demand from the seed (slab reads of any range cost only that range), so a
+# 1 M-window "file" (18 GB of examples) needs no disk or RAM: ``inference.infer_fast(..., h5=synth)``.
+_BLOCK_CACHE = {}
+
+
+class _LazyRows:
+    def __init__(self, n, make):
+        self.n, self.make = n, make
+        self.shape = (n,)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            a, b, step = idx.indices(self.n)
+            assert step == 1
+            return self.make(a, b)
+        return self.make(int(idx), int(idx) + 1)[0]
+
+
+class _SynGroup(dict):
+    def __init__(self, attrs, **datasets):
+        super().__init__(**datasets)
+        self.attrs = attrs
+
+
+class File:
+    WINDOW_STEP = 30            # windows slide by 30 positions (reference include/generate.h:21)
+
+    def __init__(self, path, mode="r", **kw):
+        assert path.startswith("synthetic://"), path
+        spec, _, query = path[len("synthetic://"):].partition("?")
+        opts = dict(kv.split("=") for kv in query.split("&") if kv)
+        self.n = int(spec)
+        self.seed = int(opts.get("seed", 1234))
+        self.contig_len = int(opts.get("contig_len", 3_000_000))
+        self.group = int(opts.get("group", 3300))          # windows per group (a 100 kb region holds ~3 300)
+        self.cache = int(opts.get("cache", 0))
+        per_contig = max(1, (self.contig_len - 90) // self.WINDOW_STEP)
+        self._root = {"contigs": _SynGroup({})}
+        first, ci = 0, 0
+        while first < self.n:
+            cn = min(per_contig, self.n - first)
+            name = f"ctg{ci}"
+            rng = np.random.Generator(np.random.PCG64(self.seed + 7919 * ci))
+            draft = "".join(np.array(list("ACGT"))[rng.integers(0, 4, size=self.contig_len)])
+            self._root["contigs"][name] = _SynGroup({"name": name, "seq": draft, "len": self.contig_len})
+            for g0 in range(0, cn, self.group):
+                gn = min(self.group, cn - g0)
+                self._root[f"{name}_{g0}"] = _SynGroup(
+                    {"contig": name, "size": gn},
+                    positions=_LazyRows(gn, lambda a, b, w0=g0: self._positions(w0 + a, w0 + b)),
+                    examples=_LazyRows(gn, lambda a, b, w0=first + g0: self._examples(w0 + a, w0 + b)))
+            first += cn
+            ci += 1
+
+    def _positions(self, a, b):
+        """Window i of a contig covers reference positions 30 i .. 30 i + 89 (no insertion slots)."""
+        start = (np.arange(a, b, dtype=np.int64) * self.WINDOW_STEP)[:, None] + np.arange(COLS, dtype=np.int64)[None, :]
+        return np.stack([start, np.zeros_like(start)], axis=2)
+
+    def _examples(self, a, b):
+        out = np.empty((b - a, READS, COLS), dtype=np.uint8)
+        blk = 4096                                             # generated in seed-addressed blocks: any range is reproducible
+        for k in range(a // blk, (b - 1) // blk + 1):
+            lo, hi = max(a, k * blk), min(b, (k + 1) * blk)
+            block = self._block(k, min(blk, self.n - k * blk))
+            out[lo - a:hi - a] = block[lo - k * blk:hi - k * blk]
+        return out
+
+    def _block(self, k, rows):
+        """Block k of the examples (4 096 windows), drawn whole so that any sub-range is reproducible: 64-bit draws viewed as
+        bytes and folded into 0..11 (the slight non-uniformity, 256 = 21 x 12 + 4, is irrelevant for a throughput workload).
+        With ``?cache=1`` blocks are kept (per process), so a second pass over the file reads memory, like a page-cached .hdf5."""
+        key = (self.seed, self.n, k)
+        if self.cache and key in _BLOCK_CACHE:
+            return _BLOCK_CACHE[key]
+        rng = np.random.Generator(np.random.PCG64(self.seed * 1_000_003 + k))
+        raw = rng.integers(0, 2 ** 63, size=(rows * READS * COLS + 7) // 8, dtype=np.uint64).view(np.uint8)[:rows * READS * COLS]
+        block = (raw % N_CODES).reshape(rows, READS, COLS)
+        if self.cache:
+            _BLOCK_CACHE[key] = block
+        return block
+
+    def keys(self):
+        return list(self._root.keys())
+
+    def __getitem__(self, k):
+        return self._root[k]
+
+    def close(self):
+        pass

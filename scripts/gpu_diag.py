@@ -23,6 +23,8 @@ CONFIGS = [
     {"name": "proj fp16 + rec fp16 + front mma.sync", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 0},
     {"name": "proj tf32 + rec tf32 + front mma.sync (round 1)", "proj": 3, "rec": 1, "rec_tc_min": 64, "front": 0},
     {"name": "default: proj fp16 + rec fp16 + front tcgen05", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 1},
+    {"name": "pingpong recurrence always", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 1, "rec_pingpong": 2},
+    {"name": "pingpong recurrence never", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 1, "rec_pingpong": 0},
 ]
 
 
@@ -55,7 +57,7 @@ def one(cfg):
     except Exception as ex:
         out["check_codes"] = repr(ex)[:120]
     h = m._handle(torch.device("cuda:0"))
-    for n in (128, 2368):
+    for n in [int(v) for v in os.environ.get("DIAG_SIZES", "128,2368").split(",")]:
         x = torch.from_numpy(uniform_windows(n, seed=3)).cuda()
         ws = torch.empty(h.lib.roko_b200_workspace_bytes(n), dtype=torch.uint8, device="cuda:0")
         labels = torch.empty((n, 90), dtype=torch.uint8, device="cuda:0")

@@ -59,8 +59,9 @@ struct roko_b200_model {
     std::mutex mu;
     unsigned long long graph_clock = 0;
     int use_graphs = 1;             // replay the chain as a CUDA graph when the batch fits the workspace (ROKO_B200_GRAPHS=0 disables)
-    int rec_pingpong = 1;           // rec_h.cu: two 32-window groups per CTA, one step out of phase: 0 never, 1 when a pass has more groups
-                                    // than CTA pairs (default), 2 always.  ROKO_B200_REC_PINGPONG
+    int rec_pingpong = 0;           // rec_h.cu: two 32-window groups per CTA, one step out of phase: 0 never (default), 1 when a pass has more
+                                    // groups than CTA pairs, 2 always.  Measured slower under full load (0.497 vs 0.408 ms at 4 736 windows):
+                                    // kept as an A/B option.  ROKO_B200_REC_PINGPONG
     int front_kind = 1;             // front end: 1 = all three contractions on tcgen05 (front_tc.cu, default); 0 = SIMT gather + warp-level
                                     // mma.sync stages (front.cu, round 1).  ROKO_B200_FRONT=tc|mma
 };

@@ -26,6 +26,13 @@ namespace roko {
 
 using namespace tc;
 
+#ifdef ROKO_TRACE      // scripts/ubench/rec_trace.cu: clock64 stamps of CTA 0's gate thread 0 and MMA lane 0
+__device__ long long roko_trace[4096];
+#define RTRACE(slot, s, g) do { if (blockIdx.x == 0 && (s) >= 20 && (s) < 24) roko_trace[((s) - 20) * 16 + (g) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define RTRACE(slot, s, g) do { } while (0)
+#endif
+
 constexpr int RH_N = 32;                         // windows per CTA pass
 constexpr int RH_GATE_THREADS = 512;             // 16 warps: TMEM lane quarter = warp & 3, window octet = warp >> 2
 constexpr int RH_WPT = RH_N / 4;                 // windows per gate thread (8)
@@ -335,12 +342,14 @@ rec_h2_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, f
                     if (g == 0) { mbar_wait(bar0 + 16, ph_d0); ph_d0 ^= 1; }
                     else        { mbar_wait(bar0 + 24, ph_d1); ph_d1 ^= 1; }
                     tc_fence_after();
+                    if (tid == 0) RTRACE(0, s, g);
                     uint32_t dr[RH_WPT], dz[RH_WPT], dn[RH_WPT];
                     const uint32_t ta = t_lane + g * (3 * RH_N);
                     ROKO_TMEM_LD8(dr, ta);
                     ROKO_TMEM_LD8(dz, ta + RH_N);
                     ROKO_TMEM_LD8(dn, ta + 2 * RH_N);
                     tmem_wait_ld();
+                    if (tid == 0) RTRACE(1, s, g);
                     const unsigned ot = obase[g] + (unsigned)(s * dt * OUT_W);
 #pragma unroll
                     for (int b = 0; b < RH_WPT; ++b) {
@@ -361,9 +370,11 @@ rec_h2_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, f
                         asm volatile("st.shared.u16 [%0], %1;" ::"r"(off + RH2_H_IMG), "h"(lo) : "memory");
                         if (b < nvalid[g]) out[ot + b * (COLS * OUT_W)] = h;
                     }
+                    if (tid == 0) RTRACE(2, s, g);
                     tc_fence_before();
                     fence_async_smem();
                     mbar_arrive(bar0 + 8 * g);
+                    if (tid == 0) RTRACE(3, s, g);
                     if (s + 1 < COLS) {
                         const unsigned on = ot + (unsigned)(dt * OUT_W);
 #pragma unroll
@@ -391,6 +402,7 @@ rec_h2_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, f
                     else        { mbar_wait(bar0 + 8, ph_h1); ph_h1 ^= 1; }
                     if (s == COLS) continue;
                     tc_fence_after();
+                    if (lane == 0) RTRACE(4, s, g);
                     const uint32_t b_hi = b_base + (2 * g) * RH2_H_IMG, b_lo = b_hi + RH2_H_IMG;
 #pragma unroll
                     for (int mt = 0; mt < 3; ++mt) {
@@ -407,6 +419,7 @@ rec_h2_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, f
                         }
                     }
                     mma_commit(bar0 + 16 + 8 * g, elected);
+                    if (lane == 0) RTRACE(5, s, g);
                     __syncwarp();
                 }
             }

@@ -82,8 +82,6 @@ int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_
  *   "rec_tc_min"    chunks of at least this many windows run the recurrence on tcgen05 (default 64; 0 = never).  Below it
  *                   the register-resident FFMA recurrence spreads few windows over many SMs for the lowest latency.
  *   "rec"           tensor-core recurrence kernel: 2 fp16-split, 48 MMAs per step (rec_h.cu, default); 1 3xTF32 (rec_tc.cu)
- *   "rec_pingpong"  rec_h.cu: two 32-window groups per CTA one step out of phase: 0 never (default: measured slower under
- *                   full load), 1 when a pass holds more groups than CTA pairs, 2 always
  *   "proj"          projection kernel: 4 tcgen05 fp16-split (proj_h.cu, default), 3 tcgen05 3xTF32, 0 FFMA SGEMM
  *   "front"         front end: 1 all contractions on tcgen05 (front_tc.cu, default), 0 SIMT gather + mma.sync (front.cu)
  *   "graphs"        replay the 8-kernel chain of roko_b200_forward_u8 as a CUDA graph (default 1; needs a non-default stream)

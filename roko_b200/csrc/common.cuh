@@ -147,7 +147,7 @@ cudaError_t launch_proj_h(const float* A, int K, const float* wimg, const float*
                           int* status, int num_sms, cudaStream_t s);
 cudaError_t proj_h_setup();
 // fp16-split recurrence (rec_h.cu): rh16_d0 = pk_rh16(l, 0), directions RH16_DIR floats apart
-cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, int pingpong, cudaStream_t s);
+cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t rec_h_setup();
 cudaError_t launch_rec_tc(const float* gi, const float* whi_d0, const float* wlo_d0, size_t dir_stride,
                           const float* bhn_d0, float* out, int nwin, int num_sms, cudaStream_t s);

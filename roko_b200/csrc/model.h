@@ -59,9 +59,6 @@ struct roko_b200_model {
     std::mutex mu;
     unsigned long long graph_clock = 0;
     int use_graphs = 1;             // replay the chain as a CUDA graph when the batch fits the workspace (ROKO_B200_GRAPHS=0 disables)
-    int rec_pingpong = 0;           // rec_h.cu: two 32-window groups per CTA, one step out of phase: 0 never (default), 1 when a pass has more
-                                    // groups than CTA pairs, 2 always.  Measured slower under full load (0.497 vs 0.408 ms at 4 736 windows):
-                                    // kept as an A/B option.  ROKO_B200_REC_PINGPONG
     int front_kind = 1;             // front end: 1 = all three contractions on tcgen05 (front_tc.cu, default); 0 = SIMT gather + warp-level
                                     // mma.sync stages (front.cu, round 1).  ROKO_B200_FRONT=tc|mma
 };
@@ -88,7 +85,7 @@ inline cudaError_t rec_dispatch(const roko_b200_model* m, const float* gi, int l
     using namespace roko;
     const float* pk = m->packed;
     if (m->rec_tc_min > 0 && nc >= m->rec_tc_min) {
-        if (m->rec_kind == 2) return launch_rec_h(gi, pk + pk_rh16(l, 0), out, nc, m->num_sms, m->rec_pingpong, s);
+        if (m->rec_kind == 2) return launch_rec_h(gi, pk + pk_rh16(l, 0), out, nc, m->num_sms, s);
         if (nc >= 64)       // (>= 64 windows keeps rec_tc's unguarded gi reads of a ragged last group inside the scratch)
             return launch_rec_tc(gi, pk + pk_rtc(l, 0), pk + pk_rtc(l, 0) + RTC_W, (size_t)RTC_DIR, pk + pk_rtc(l, 0) + 2 * RTC_W,
                                  out, nc, m->num_sms, s);

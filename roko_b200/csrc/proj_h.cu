@@ -227,6 +227,7 @@ proj_h_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const
     }
 }
 
+
 cudaError_t proj_h_setup() {
     cudaError_t e = cudaFuncSetAttribute(proj_h_kernel<IN0P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM);
     if (e != cudaSuccess) return e;

@@ -28,9 +28,9 @@ using namespace tc;
 
 #ifdef ROKO_TRACE      // scripts/ubench/rec_trace.cu: clock64 stamps of CTA 0's gate thread 0 and MMA lane 0
 __device__ long long roko_trace[4096];
-#define RTRACE(slot, s, g) do { if (blockIdx.x == 0 && (s) >= 20 && (s) < 24) roko_trace[((s) - 20) * 16 + (g) * 8 + (slot)] = clock64(); } while (0)
+#define RTRACE(slot, s) do { if (blockIdx.x == 0 && (s) >= 20 && (s) < 24) roko_trace[((s) - 20) * 8 + (slot)] = clock64(); } while (0)
 #else
-#define RTRACE(slot, s, g) do { } while (0)
+#define RTRACE(slot, s) do { } while (0)
 #endif
 
 constexpr int RH_N = 32;                         // windows per CTA pass
@@ -143,6 +143,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 uint32_t a0[RH_WPT], a1[RH_WPT], b0[RH_WPT], b1[RH_WPT];
                 mbar_wait(bar_rz, ph);
                 tc_fence_after();
+                if (tid == 0) RTRACE(0, s);
                 ROKO_TMEM_LD8(a0, t_lane);                          // r: hi.hi + lo.hi
                 ROKO_TMEM_LD8(a1, t_lane + RH_N);                   // r: hi.lo
                 ROKO_TMEM_LD8(b0, t_lane + 2 * RH_N);               // z
@@ -159,8 +160,10 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                     const float rc = rcpf(ea * eb);
                     rr[b] = rc * eb; zz[b] = rc * ea;
                 }
+                if (tid == 0) RTRACE(1, s);
                 mbar_wait(bar_n, ph); ph ^= 1;
                 tc_fence_after();
+                if (tid == 0) RTRACE(2, s);
                 ROKO_TMEM_LD8(a0, t_lane + 4 * RH_N);               // n
                 ROKO_TMEM_LD8(a1, t_lane + 5 * RH_N);
                 tmem_wait_ld();
@@ -179,6 +182,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 tc_fence_before();
                 fence_async_smem();
                 mbar_arrive(bar_h);                                 // h_t is in shared memory, D has been consumed
+                if (tid == 0) RTRACE(3, s);
                 if (s + 1 < COLS) {                                 // lands while the tensor core runs the next step
 #pragma unroll
                     for (int b = 0; b < RH_WPT; ++b) {
@@ -202,6 +206,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 mbar_wait(bar_h, ph_h); ph_h ^= 1;
                 if (s == COLS) break;                               // the last arrival only closes the pass
                 tc_fence_after();
+                if (lane == 0) RTRACE(4, s);
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {              // r, z tiles first, committed on their own
 #pragma unroll
@@ -217,6 +222,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                     }
                     mma_commit(part ? bar_n : bar_rz, elected);
                 }
+                if (lane == 0) RTRACE(5, s);
                 __syncwarp();
             }
         }
@@ -230,226 +236,14 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
 }
 
 
-// ---- two groups per CTA, ping-ponged (large passes) --------------------------------------------------------------
-// With more than 32 x (SMs / 2) windows in a pass every CTA has several 32-window groups to do anyway; this variant
-// runs TWO of them one step out of phase, so that the gate math of one group (MUFU-bound, ~2k cycles) overlaps the
-// MMAs of the other and the serial chain per step shrinks from  MMA + gates  to  max(MMA, gates).  Tensor memory:
-// W_hi 192 columns + 2 x (3 gates x 32 columns); no N-concatenation here (it would need 2 x 192 accumulator columns),
-// so a group-step is 72 MMAs: W_hi.h_lo, W_hi.h_hi from tensor memory, W_lo.h_hi from shared memory.
-constexpr int RH2_D0 = 3 * (HID / 2);                             // 192: D of group g, gate tile mt at 192 + 96 g + 32 mt
-constexpr int RH2_H_IMG = RH_N * HID * 2;                         // 8 192 B: one hi (or lo) image of a group, [k atom 2][32 rows][128 B]
-constexpr int RH2_SMEM = RH_WLO_BYTES + 4 * RH2_H_IMG + 1024 + 64;
-
-__global__ void __launch_bounds__(RH_THREADS, 1)
-rec_h2_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, float* __restrict__ out, int nwin) {
-    extern __shared__ unsigned char rh_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)rh_smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* s_wlo = smem;
-    unsigned char* s_h = smem + RH_WLO_BYTES;                       // [group][hi|lo] images
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + 4 * RH2_H_IMG);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    const uint32_t bar0 = smem_u32(bars);                           // h_ready[g] = bar0 + 8 g, d_ready[g] = bar0 + 16 + 8 g, w = bar0 + 32
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int dir = blockIdx.x & 1;
-    const float* wimg = rh16_d0 + (size_t)dir * RH16_DIR;
-
-    if (tid == 0) {
-        mbar_init(bar0, RH_GATE_THREADS);
-        mbar_init(bar0 + 8, RH_GATE_THREADS);
-        mbar_init(bar0 + 16, 1);
-        mbar_init(bar0 + 24, 1);
-        mbar_init(bar0 + 32, 1);
-        mbar_init_fence();
-    }
-    if (warp == RH_GATE_THREADS / 32) tmem_alloc<RH_TMEM_COLS>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (tid == RH_GATE_THREADS) {                                   // W_lo image -> shared memory (bulk copies)
-        mbar_expect_tx(bar0 + 32, RH_WLO_BYTES);
-        for (int c = 0; c < 3; ++c)
-            bulk_g2s(smem_u32(s_wlo) + c * 32768, reinterpret_cast<const unsigned char*>(wimg + RH16_W / 2) + c * 32768, 32768, bar0 + 32);
-    }
-    if (warp < 4) {                                                 // W_hi -> tensor memory
-        const int row = warp * 32 + lane;
-#pragma unroll 1
-        for (int mt = 0; mt < 3; ++mt) {
-            const uint4* src = reinterpret_cast<const uint4*>(wimg + ((size_t)mt * HID + row) * (HID / 2));
-#pragma unroll
-            for (int c0 = 0; c0 < HID / 2; c0 += 32) {
-                uint32_t v[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint4 f = __ldg(src + c0 / 4 + q);
-                    v[q * 4 + 0] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
-                }
-                ROKO_TMEM_ST32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(RH_A_HI + mt * (HID / 2) + c0), v);
-            }
-        }
-        tmem_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    const int npass = (nwin + 2 * RH_N - 1) / (2 * RH_N);           // a pass = 64 windows = two groups
-
-    if (warp < RH_GATE_THREADS / 32) {
-        // ================================ gate threads ==============================================
-        const int q = warp & 3, oct = warp >> 2;
-        const int j = q * 32 + lane;
-        const float bhn = wimg[RH16_W + j];
-        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + RH2_D0 + oct * RH_WPT;
-        // H image element (row = oct * 8 + b, k = j): row & 7 == b, so the swizzled chunk is ((j & 63) >> 3) ^ b
-        const uint32_t hs = smem_u32(s_h) + (uint32_t)(j >> 6) * (RH_N * 128) + (uint32_t)oct * 1024 + (uint32_t)(j & 7) * 2;
-        const uint32_t chunk = (uint32_t)(j & 63) >> 3;
-        const int dt = dir ? -1 : 1;
-        uint32_t ph_d0 = 0, ph_d1 = 0;
-        for (int pass = blockIdx.x >> 1; pass < npass; pass += gridDim.x >> 1) {
-            const int t0 = dir ? COLS - 1 : 0;
-            // window b of group g: w = pass * 64 + g * 32 + oct * 8 + b, clamped to the batch (clamped rows are never stored);
-            // out offset o = (w * 90 + t) * 256 + dir * 128 + j; the gate-interleaved gi offset is exactly 3 o
-            unsigned obase[2];
-            int nvalid[2];
-            float hprev[2][RH_WPT], g_r[2][RH_WPT], g_z[2][RH_WPT], g_n[2][RH_WPT];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int w0 = pass * (2 * RH_N) + g * RH_N + oct * RH_WPT;
-                nvalid[g] = nwin - w0;                              // windows b < nvalid exist (may be <= 0)
-                const int wb = w0 < nwin ? w0 : nwin - 1;
-                obase[g] = (unsigned)(wb * COLS + t0) * OUT_W + dir * HID + j;
-#pragma unroll
-                for (int b = 0; b < RH_WPT; ++b) {
-                    const unsigned o = obase[g] + (b < nvalid[g] ? b : 0) * (COLS * OUT_W);
-                    hprev[g][b] = 0.f;
-                    const uint32_t off = hs + (2 * g) * RH2_H_IMG + b * 128 + ((chunk ^ (uint32_t)b) << 4);
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(off), "h"((unsigned short)0) : "memory");
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(off + RH2_H_IMG), "h"((unsigned short)0) : "memory");
-                    const float* gp = gi + 3u * o;
-                    g_r[g][b] = __ldg(gp); g_z[g][b] = __ldg(gp + 1); g_n[g][b] = __ldg(gp + 2);
-                }
-            }
-            fence_async_smem();
-            mbar_arrive(bar0);
-            mbar_arrive(bar0 + 8);
-#pragma unroll 1
-            for (int s = 0; s < COLS; ++s) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (g == 0) { mbar_wait(bar0 + 16, ph_d0); ph_d0 ^= 1; }
-                    else        { mbar_wait(bar0 + 24, ph_d1); ph_d1 ^= 1; }
-                    tc_fence_after();
-                    if (tid == 0) RTRACE(0, s, g);
-                    uint32_t dr[RH_WPT], dz[RH_WPT], dn[RH_WPT];
-                    const uint32_t ta = t_lane + g * (3 * RH_N);
-                    ROKO_TMEM_LD8(dr, ta);
-                    ROKO_TMEM_LD8(dz, ta + RH_N);
-                    ROKO_TMEM_LD8(dn, ta + 2 * RH_N);
-                    tmem_wait_ld();
-                    if (tid == 0) RTRACE(1, s, g);
-                    const unsigned ot = obase[g] + (unsigned)(s * dt * OUT_W);
-#pragma unroll
-                    for (int b = 0; b < RH_WPT; ++b) {
-                        const float xr = fmaxf(fmaf(__uint_as_float(dr[b]), RH_INV, g_r[g][b]), -40.f);
-                        const float xz = fmaxf(fmaf(__uint_as_float(dz[b]), RH_INV, g_z[g][b]), -40.f);
-                        const float ea = 1.f + ex2f(-1.4426950408889634f * xr);
-                        const float eb = 1.f + ex2f(-1.4426950408889634f * xz);
-                        const float rc = rcpf(ea * eb);
-                        const float r = rc * eb, z = rc * ea;
-                        const float xn = fmaf(r, fmaf(__uint_as_float(dn[b]), RH_INV, bhn), g_n[g][b]);
-                        const float n = fmaf(2.f, rcpf(1.f + ex2f(-2.8853900817779268f * xn)), -1.f);
-                        const float h = fmaf(z, hprev[g][b] - n, n);
-                        hprev[g][b] = h;
-                        unsigned short hi, lo;
-                        split_f16(h * H_SCALE, hi, lo);
-                        const uint32_t off = hs + (2 * g) * RH2_H_IMG + b * 128 + ((chunk ^ (uint32_t)b) << 4);
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off), "h"(hi) : "memory");
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off + RH2_H_IMG), "h"(lo) : "memory");
-                        if (b < nvalid[g]) out[ot + b * (COLS * OUT_W)] = h;
-                    }
-                    if (tid == 0) RTRACE(2, s, g);
-                    tc_fence_before();
-                    fence_async_smem();
-                    mbar_arrive(bar0 + 8 * g);
-                    if (tid == 0) RTRACE(3, s, g);
-                    if (s + 1 < COLS) {
-                        const unsigned on = ot + (unsigned)(dt * OUT_W);
-#pragma unroll
-                        for (int b = 0; b < RH_WPT; ++b) {
-                            const float* gp = gi + 3u * (on + (b < nvalid[g] ? b : 0) * (COLS * OUT_W));
-                            g_r[g][b] = __ldg(gp); g_z[g][b] = __ldg(gp + 1); g_n[g][b] = __ldg(gp + 2);
-                        }
-                    }
-                }
-            }
-        }
-    } else {
-        // ================================ MMA issuer (whole warp, uniform) ==========================
-        if (tmem != 0) __trap();
-        mbar_wait(bar0 + 32, 0);
-        const uint32_t a_lo = smem_u32(s_wlo), b_base = smem_u32(s_h);
-        const uint32_t elected = elect_one();
-        uint32_t ph_h0 = 0, ph_h1 = 0;
-        for (int pass = blockIdx.x >> 1; pass < npass; pass += gridDim.x >> 1) {
-#pragma unroll 1
-            for (int s = 0; s <= COLS; ++s) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (g == 0) { mbar_wait(bar0, ph_h0); ph_h0 ^= 1; }
-                    else        { mbar_wait(bar0 + 8, ph_h1); ph_h1 ^= 1; }
-                    if (s == COLS) continue;
-                    tc_fence_after();
-                    if (lane == 0) RTRACE(4, s, g);
-                    const uint32_t b_hi = b_base + (2 * g) * RH2_H_IMG, b_lo = b_hi + RH2_H_IMG;
-#pragma unroll
-                    for (int mt = 0; mt < 3; ++mt) {
-                        const uint32_t d = RH2_D0 + g * (3 * RH_N) + mt * RH_N;
-#pragma unroll
-                        for (int kk = 0; kk < HID / 16; ++kk) {
-                            const uint32_t koff = (uint32_t)(kk >> 2) * (RH_N * 128) + (uint32_t)(kk & 3) * 32;
-                            const uint64_t dbh = desc_sw128(b_hi + koff), dbl = desc_sw128(b_lo + koff);
-                            const uint64_t da = desc_sw128(a_lo + (uint32_t)mt * 32768 + (uint32_t)(kk >> 2) * 16384 + (uint32_t)(kk & 3) * 32);
-                            const uint32_t a_hi = RH_A_HI + mt * (HID / 2) + kk * 8;
-                            mma_f16_ss(d, da, dbh, RH_ID32, kk ? 1u : 0u, elected);      // W_lo h_hi   (small terms first)
-                            mma_f16_ts(d, a_hi, dbl, RH_ID32, 1u, elected);              // W_hi h_lo
-                            mma_f16_ts(d, a_hi, dbh, RH_ID32, 1u, elected);              // W_hi h_hi
-                        }
-                    }
-                    mma_commit(bar0 + 16 + 8 * g, elected);
-                    if (lane == 0) RTRACE(5, s, g);
-                    __syncwarp();
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == RH_GATE_THREADS / 32) {
-        tc_fence_after();
-        tmem_dealloc<RH_TMEM_COLS>(tmem);
-    }
-}
-
 cudaError_t rec_h_setup() {
-    cudaError_t e = cudaFuncSetAttribute(rec_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rec_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH2_SMEM);
+    return cudaFuncSetAttribute(rec_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_SMEM);
 }
 
-// pingpong: 0 never, 1 when the pass has more 32-window groups than CTA pairs (default), 2 always
-cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, int pingpong, cudaStream_t s) {
+cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
-    const int pairs = num_sms / 2;
     const int npass = (nwin + RH_N - 1) / RH_N;
-    if (pingpong == 2 || (pingpong == 1 && npass > pairs)) {
-        const int npass2 = (nwin + 2 * RH_N - 1) / (2 * RH_N);
-        const int grid = 2 * (npass2 < pairs ? npass2 : pairs);
-        rec_h2_kernel<<<grid, RH_THREADS, RH2_SMEM, s>>>(gi, rh16_d0, out, nwin);
-        return cudaGetLastError();
-    }
+    const int pairs = num_sms / 2;
     const int grid = 2 * (npass < pairs ? npass : pairs);
     rec_h_kernel<<<grid, RH_THREADS, RH_SMEM, s>>>(gi, rh16_d0, out, nwin);
     return cudaGetLastError();

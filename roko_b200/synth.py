@@ -67,7 +67,18 @@ class _SynGroup(dict):
         self.attrs = attrs
 
 
-class File:
+_FILES = {}
+
+
+def File(path, mode="r", **kw):
+    """h5py.File stand-in: files are immutable functions of their path, so one object per process serves every open."""
+    f = _FILES.get(path)
+    if f is None:
+        f = _FILES[path] = _File(path)
+    return f
+
+
+class _File:
     WINDOW_STEP = 30            # windows slide by 30 positions (reference include/generate.h:21)
 
     def __init__(self, path, mode="r", **kw):

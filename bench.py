@@ -342,33 +342,37 @@ def run_ours(args):
     with torch.no_grad():
         run_steps(W, labels_all)
         torch.cuda.synchronize()
-        # calibration: how many K-step blocks make a timed region of >= min_region seconds
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(main)
+        # The timed region is R blocks of exactly K steps, back to back (no sync between blocks).  R starts from a calibration
+        # block and is raised until the region lasts >= min_region seconds (the first blocks also pay the CUDA-graph captures).
         block(0)
-        c1.record(main)
         torch.cuda.synchronize()
-        R = max(1, min(args.max_blocks, int(np.ceil(args.min_region * 1e3 / max(c0.elapsed_time(c1), 1e-3)))))
-        if world > 1:
-            t = torch.tensor([R], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            R = int(t.item())
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
             time.sleep(0.12)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tw0 = time.perf_counter()
-        e0.record(main)
-        gathered = None
-        for r in range(R):                               # R blocks of exactly K steps, back to back (no sync between)
-            gathered = block(r * K)
-        e1.record(main)
-        torch.cuda.synchronize()
-        tw1 = time.perf_counter()
+        R, regions = 8, []
+        for attempt in range(4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tw0 = time.perf_counter()
+            e0.record(main)
+            gathered = None
+            for r in range(R):
+                gathered = block(r * K)
+            e1.record(main)
+            torch.cuda.synchronize()
+            tw1 = time.perf_counter()
+            ms_try = e0.elapsed_time(e1)
+            if world > 1:                                # every rank takes the same decision
+                t = torch.tensor([ms_try], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_try = float(t.item())
+            regions.append((tw0, tw1))
+            if ms_try >= args.min_region * 1e3 * 0.95 or R >= args.max_blocks:
+                break
+            R = min(args.max_blocks, int(np.ceil(R * args.min_region * 1e3 / max(ms_try, 1e-3) * 1.15)))
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -429,7 +433,7 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = calls * Kh * batch * world / e2e_s
     # clocks sampled inside the two timed regions (device-resident steps, end-to-end calls)
-    clocks = sampler.stop([(tw0, tw1), (t0, t0 + e2e_s)]) if rank == 0 else None
+    clocks = sampler.stop([regions[-1], (t0, t0 + e2e_s)]) if rank == 0 else None
     del x_host
 
     # ---- per-kernel device times (CUDA events between the kernels of the chain) -> roofline --------

@@ -261,7 +261,7 @@ int roko_b200_model_create(roko_b200_model** out, int device) {
     if (e == cudaSuccess) e = rec_h_setup();
     if (const char* rt = getenv("ROKO_B200_REC_TC_MIN")) m->rec_tc_min = atoi(rt);
     if (const char* sb = getenv("ROKO_B200_SUPERBATCH")) m->superbatch = atoi(sb) > 0 ? atoi(sb) : 1;
-    if (const char* pj = getenv("ROKO_B200_PROJ")) m->use_tc = strcmp(pj, "ffma") == 0 ? 0 : (strcmp(pj, "tf32") == 0 ? 3 : (strcmp(pj, "fp16x2") == 0 ? 5 : 4));
+    if (const char* pj = getenv("ROKO_B200_PROJ")) m->use_tc = strcmp(pj, "ffma") == 0 ? 0 : (strcmp(pj, "tf32") == 0 ? 3 : 4);
     if (const char* rk = getenv("ROKO_B200_REC")) m->rec_kind = strcmp(rk, "tf32") == 0 ? 1 : 2;
     if (const char* gr = getenv("ROKO_B200_GRAPHS")) m->use_graphs = atoi(gr);
     if (const char* fr = getenv("ROKO_B200_FRONT")) m->front_kind = strcmp(fr, "tc") == 0 ? 1 : 0;
@@ -435,7 +435,7 @@ int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long v
     }
     if (strcmp(name, "rec_tc_min") == 0) { m->rec_tc_min = (int)value; return ROKO_B200_OK; }
     if (strcmp(name, "superbatch") == 0) { if (value < 1) return fail(ROKO_B200_EARG, "superbatch < 1%s%s"); m->superbatch = (int)value; return ROKO_B200_OK; }
-    if (strcmp(name, "proj") == 0) { if (value != 0 && value != 3 && value != 4 && value != 5) return fail(ROKO_B200_EARG, "proj must be 0 (ffma), 3 (tf32), 4 (fp16) or 5 (fp16, CTA pairs)%s%s"); m->use_tc = (int)value; return ROKO_B200_OK; }
+    if (strcmp(name, "proj") == 0) { if (value != 0 && value != 3 && value != 4) return fail(ROKO_B200_EARG, "proj must be 0 (ffma), 3 (tf32) or 4 (fp16)%s%s"); m->use_tc = (int)value; return ROKO_B200_OK; }
     if (strcmp(name, "rec") == 0) { if (value != 1 && value != 2) return fail(ROKO_B200_EARG, "rec must be 1 (tf32) or 2 (fp16)%s%s"); m->rec_kind = (int)value; return ROKO_B200_OK; }
     if (strcmp(name, "graphs") == 0) { m->use_graphs = value != 0; return ROKO_B200_OK; }
     if (strcmp(name, "front") == 0) { if (value != 0 && value != 1) return fail(ROKO_B200_EARG, "front must be 0 (mma.sync) or 1 (tcgen05)%s%s"); m->front_kind = (int)value; return ROKO_B200_OK; }

@@ -146,8 +146,6 @@ cudaError_t proj_tc3_setup();
 cudaError_t launch_proj_h(const float* A, int K, const float* wimg, const float* bias, float* C, int M, float in_scale,
                           int* status, int num_sms, cudaStream_t s);
 cudaError_t proj_h_setup();
-cudaError_t launch_proj_h2(const float* A, int K, const float* wimg, const float* bias, float* C, int M, float in_scale,
-                           int* status, int num_sms, cudaStream_t s);
 // fp16-split recurrence (rec_h.cu): rh16_d0 = pk_rh16(l, 0), directions RH16_DIR floats apart
 cudaError_t launch_rec_h(const float* gi, const float* rh16_d0, float* out, int nwin, int num_sms, cudaStream_t s);
 cudaError_t rec_h_setup();

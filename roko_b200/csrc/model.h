@@ -73,9 +73,6 @@ inline cudaError_t proj_dispatch(const roko_b200_model* m, const float* in, int 
                                  cudaStream_t s) {
     using namespace roko;
     const float* pk = m->packed;
-    if (m->use_tc == 5)
-        return launch_proj_h2(in, gru_inp(l), pk + pk_wh16(l), pk + pk_bgi(l), gi, rows, l == 0 ? tc::U_SCALE : tc::H_SCALE,
-                              m->status, m->num_sms, s);
     if (m->use_tc == 4)
         return launch_proj_h(in, gru_inp(l), pk + pk_wh16(l), pk + pk_bgi(l), gi, rows, l == 0 ? tc::U_SCALE : tc::H_SCALE,
                              m->status, m->num_sms, s);

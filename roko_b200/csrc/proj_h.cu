@@ -29,7 +29,7 @@ constexpr int PH_SMEM = PH_STAGES * PH_STAGE + 1024 + 256 + PH_EPI_BYTES;
 constexpr int PH_TMEM_COLS = 512;
 constexpr uint32_t PH_IDESC = idesc_f16(TC_BM, TC_BN);
 
-// A producers, shared by both projection kernels: 256 threads turn fp32 activation rows into the fp16 hi / lo K-major swizzled
+// A producers: 256 threads turn fp32 activation rows into the fp16 hi / lo K-major swizzled
 // images of one k block (128 rows x 64 k) per pipeline stage.  thread = (16-byte chunk of 8 fp16 = 8 consecutive k, rows rr + 32 i).
 // TWO k blocks of loads are in flight per thread: with one, the loop was bound by the latency of its own loads (3.9 k cycles per
 // k block against 1.5 k of MMA work: ncu `long_scoreboard` 7 warps per issue, L2 -> SM path at 60 %).
@@ -244,202 +244,10 @@ proj_h_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const
 
 
 
-// ---- CTA-pair variant: tcgen05 cta_group::2 -------------------------------------------------------------------------
-// proj_h_kernel is bound by what one SM can ingest from L2 (23-25 B/clk: profiles/r02_ncu_summary.md): every 128 x 256 tile pulls
-// its 128 rows of activations AND all 256 rows of the W_ih tile.  Here two CTAs of a cluster work on the SAME n tile and on two
-// adjacent 128-row blocks: each CTA stages its own activation rows and only HALF of the W tile (128 of its 256 rows); the leader
-// CTA issues M = 256 / N = 256 MMAs with cta_group::2, for which the tensor cores read the B operand from both CTAs' shared
-// memory and write rows 0-127 / 128-255 of the accumulator into the leader's / the peer's tensor memory.  Operand ingest per SM
-// and output drops from 11.7 to 8 bytes, and a stage shrinks to 64 KB, so three stages fit.
-// Hand-overs across the pair: A images and W halves report to the LEADER's barriers (the peer's producers arrive remotely, the
-// peer's W loader relays its local bulk-copy barrier), tcgen05.commit multicasts "stage free" / "accumulator full" to both CTAs,
-// and both epilogues report "accumulator drained" to the leader.  (cta_group::2 semantics probed in scripts/ubench/cta2_gemm.cu.)
-constexpr int P2_STAGES = 3;
-constexpr int P2_W_IMG = 128 * H16_BK * 2;                // 16 KB: this CTA's half of the W tile, hi or lo
-constexpr int P2_STAGE = 2 * PH_A_IMG + 2 * P2_W_IMG;     // 64 KB
-constexpr int P2_SMEM = P2_STAGES * P2_STAGE + 1024 + 256 + PH_EPI_BYTES;
-constexpr uint32_t P2_IDESC = idesc_f16(256, TC_BN);
-static_assert(P2_SMEM <= 232448, "shared memory budget");
-
-template <int K>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PH_THREADS, 1)
-proj_h2_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const float* __restrict__ bias,
-               float* __restrict__ C, int M, int ntiles, float in_scale, int* __restrict__ status) {
-    constexpr int KB = K / H16_BK;
-    extern __shared__ unsigned char ph_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)ph_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P2_STAGES * P2_STAGE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    float* epi_stage = reinterpret_cast<float*>(smem + P2_STAGES * P2_STAGE + 256);
-    const uint32_t sbase = smem_u32(smem), bar0 = smem_u32(bars);
-    // barriers (per CTA; "L" = only the leader's instance is waited on):
-    //   full_a[s] = s (L, 512 arrivals: both CTAs' producers)   w_local[s] = 3+s (own bulk copy)   w_peer[s] = 6+s (L, peer's relay)
-    //   empty[s] = 9+s (commit, multicast)   acc_full[b] = 12+b (commit, multicast)   acc_empty[b] = 14+b (L, 256 arrivals)
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < P2_STAGES; ++s) {
-            mbar_init(BAR(s), 512);
-            mbar_init(BAR(3 + s), 1);
-            mbar_init(BAR(6 + s), 1);
-            mbar_init(BAR(9 + s), 1);
-        }
-        for (int b = 0; b < 2; ++b) { mbar_init(BAR(12 + b), 1); mbar_init(BAR(14 + b), 256); }
-        mbar_init_fence();
-    }
-    if (warp == 9) tmem_alloc2<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();                                               // both CTAs' barriers exist before anyone arrives remotely
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-
-    if (warp < 8) {
-        // ------------------------------- A producers (own 128 rows; produce_a above) ----------------
-        uint32_t full_remote[P2_STAGES];
-#pragma unroll
-        for (int s = 0; s < P2_STAGES; ++s) full_remote[s] = mapa(BAR(s), 0);
-        const int mine = (ntiles - pair + npairs - 1) / npairs;
-        produce_a<K, P2_STAGES>(A, M, mine, [&](int j) { return ((pair + j * npairs) / 3) * 256 + (int)rank * TC_BM; }, smem, P2_STAGE,
-                                BAR(9), in_scale, status, [&](int s_) { mbar_arrive_cluster(full_remote[s_]); }, tid);   // the leader's MMA warp waits for both CTAs' images
-    } else if (warp == 8) {
-        // ------------------------------- W loader: this CTA's half of the W tile ----------------------
-        if (lane == 0) {
-            int it = 0;
-            uint32_t peer_remote[P2_STAGES];
-#pragma unroll
-            for (int s = 0; s < P2_STAGES; ++s) peer_remote[s] = mapa(BAR(6 + s), 0);
-            auto relay = [&](int done) {                           // peer only: tell the leader that my half of k block `done` has landed
-                if (rank == 1) {
-                    const int s = done % P2_STAGES;
-                    mbar_wait(BAR(3 + s), (done / P2_STAGES) & 1);
-                    mbar_arrive_cluster(peer_remote[s]);
-                }
-            };
-            for (int tile = pair; tile < ntiles; tile += npairs) {
-                // rows 128 rank .. 128 rank + 127 of every 256-row image are one contiguous 16 KB block
-                const float* src = wimg + (size_t)(tile % 3) * KB * 2 * H16_IMG + rank * (P2_W_IMG / 4);
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % P2_STAGES;
-                    mbar_wait(BAR(9 + s), ((it / P2_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(BAR(3 + s), 2 * P2_W_IMG);
-                    const uint32_t dst = sbase + s * P2_STAGE + 2 * PH_A_IMG;
-                    bulk_g2s(dst, src + (size_t)(kb * 2) * H16_IMG, P2_W_IMG, BAR(3 + s));
-                    bulk_g2s(dst + P2_W_IMG, src + (size_t)(kb * 2 + 1) * H16_IMG, P2_W_IMG, BAR(3 + s));
-                    if (it > 0) relay(it - 1);
-                }
-            }
-            if (it > 0) relay(it - 1);
-        }
-    } else if (warp == 9) {
-        // ------------------------------- MMA issuer: leader CTA only ----------------------------------
-        if (tmem_d != 0) __trap();
-        if (rank == 0) {
-            const uint32_t elected = elect_one();
-            int it = 0, j = 0;
-            for (int tile = pair; tile < ntiles; tile += npairs, ++j) {
-                const uint32_t buf = j & 1;
-                mbar_wait_cluster(BAR(14 + buf), ((j >> 1) & 1) ^ 1);   // both epilogues have drained this accumulator
-                tc_fence_after();
-                const uint32_t d = buf * TC_BN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % P2_STAGES;
-                    const uint32_t ph = (it / P2_STAGES) & 1;
-                    mbar_wait_cluster(BAR(s), ph);                   // both CTAs' A images
-                    mbar_wait(BAR(3 + s), ph);                       // my half of W
-                    mbar_wait_cluster(BAR(6 + s), ph);               // the peer's half of W
-                    tc_fence_after();
-                    const uint32_t a_hi = sbase + s * P2_STAGE, a_lo = a_hi + PH_A_IMG;
-                    const uint32_t w_hi = a_lo + PH_A_IMG, w_lo = w_hi + P2_W_IMG;
-#pragma unroll
-                    for (int kk = 0; kk < H16_BK / 16; ++kk) {
-                        const uint64_t dah = desc_sw128(a_hi + kk * 32), dal = desc_sw128(a_lo + kk * 32);
-                        const uint64_t dwh = desc_sw128(w_hi + kk * 32), dwl = desc_sw128(w_lo + kk * 32);
-                        mma2_f16_ss(d, dal, dwh, P2_IDESC, (kb | kk) ? 1u : 0u, elected);   // small terms first
-                        mma2_f16_ss(d, dah, dwl, P2_IDESC, 1u, elected);
-                        mma2_f16_ss(d, dah, dwh, P2_IDESC, 1u, elected);
-                    }
-                    mma2_commit(BAR(9 + s), elected);                // stage free, in both CTAs
-                    __syncwarp();
-                }
-                mma2_commit(BAR(12 + buf), elected);                 // accumulator complete, in both CTAs
-                __syncwarp();
-            }
-        }
-    } else {
-        // ------------------------------- epilogue warps (10..13): own 128 rows ------------------------
-        const int q = warp & 3;
-        const float inv = 1.f / (W_SCALE * in_scale);
-        float* T = epi_stage + (warp - 10) * 32 * PH_EPI_ROW;
-        const int rsub = lane >> 3, csub = (lane & 7) * 4;
-        const uint32_t drained[2] = {mapa(BAR(14), 0), mapa(BAR(15), 0)};
-        int j = 0;
-        for (int tile = pair; tile < ntiles; tile += npairs, ++j) {
-            const uint32_t buf = j & 1;
-            const int m0 = (tile / 3) * 256 + (int)rank * TC_BM, n_tile = tile % 3;
-            mbar_wait(BAR(12 + buf), (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * TC_BN;
-            const float* brow = bias + n_tile * TC_BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                uint32_t r[32];
-                ROKO_TMEM_LD32(r, taddr + (uint32_t)c0);
-                tmem_wait_ld();
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq)
-                    *reinterpret_cast<float4*>(T + lane * PH_EPI_ROW + qq * 4) =
-                        make_float4(__uint_as_float(r[qq * 4 + 0]), __uint_as_float(r[qq * 4 + 1]),
-                                    __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
-                __syncwarp();
-                const float4 b = __ldg(reinterpret_cast<const float4*>(brow + c0 + csub));
-#pragma unroll
-                for (int i8 = 0; i8 < 8; ++i8) {
-                    const int rr = i8 * 4 + rsub;
-                    const int m = m0 + q * 32 + rr;
-                    float4 v = *reinterpret_cast<const float4*>(T + rr * PH_EPI_ROW + csub);
-                    v.x = fmaf(v.x, inv, b.x); v.y = fmaf(v.y, inv, b.y); v.z = fmaf(v.z, inv, b.z); v.w = fmaf(v.w, inv, b.w);
-                    if (m < M) *reinterpret_cast<float4*>(C + (size_t)m * GI_N + n_tile * TC_BN + c0 + csub) = v;
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            mbar_arrive_cluster(drained[buf]);                       // the leader may overwrite this accumulator (in both CTAs)
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync();                                               // the peer's tensor memory is in use until the leader's last MMA retired
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc2<512>(tmem_d);
-    }
-}
-
 cudaError_t proj_h_setup() {
     cudaError_t e = cudaFuncSetAttribute(proj_h_kernel<IN0P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(proj_h_kernel<OUT_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(proj_h2_kernel<IN0P>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(proj_h2_kernel<OUT_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
-}
-
-// CTA-pair projection (cta_group::2): tiles are 256 rows x 256 columns per pair
-cudaError_t launch_proj_h2(const float* A, int K, const float* wimg, const float* bias, float* C, int M, float in_scale,
-                           int* status, int num_sms, cudaStream_t s) {
-    if (M <= 0) return cudaSuccess;
-    const int ntiles = ((M + 255) / 256) * (GI_N / TC_BN);
-    const int pairs = num_sms / 2;
-    const int grid = 2 * (ntiles < pairs ? ntiles : pairs);
-    if (K == IN0P) proj_h2_kernel<IN0P><<<grid, PH_THREADS, P2_SMEM, s>>>(A, wimg, bias, C, M, ntiles, in_scale, status);
-    else if (K == OUT_W) proj_h2_kernel<OUT_W><<<grid, PH_THREADS, P2_SMEM, s>>>(A, wimg, bias, C, M, ntiles, in_scale, status);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    return cudaFuncSetAttribute(proj_h_kernel<OUT_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM);
 }
 
 cudaError_t launch_proj_h(const float* A, int K, const float* wimg, const float* bias, float* C, int M, float in_scale,

@@ -23,7 +23,6 @@ CONFIGS = [
     {"name": "proj fp16 + rec fp16 + front mma.sync", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 0},
     {"name": "proj tf32 + rec tf32 + front mma.sync (round 1)", "proj": 3, "rec": 1, "rec_tc_min": 64, "front": 0},
     {"name": "default: proj fp16 + rec fp16 + front tcgen05", "proj": 4, "rec": 2, "rec_tc_min": 32, "front": 1},
-    {"name": "CTA-pair projection (cta_group::2)", "proj": 5, "rec": 2, "rec_tc_min": 32, "front": 1},
 ]
 
 

@@ -12,6 +12,8 @@
 using namespace roko::tc;
 
 constexpr int M = 256, N = 128, K = 64;
+// Result on B200: correct in both modes.  The full CTA-pair projection built on it (proj_h2_kernel, git history: the commit before
+// this file's last change) was also correct but slower than the single-CTA kernel (0.526 / 0.298 vs 0.422 / 0.257 ms per layer).
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {

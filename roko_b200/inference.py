@@ -42,7 +42,10 @@ N_LABELS = 5          # classes the network emits: A C G T *
 MAX_INS = 3           # insertion slots per reference position (reference include/generate.h:22)
 
 
-def _h5():
+def _h5(path=None):
+    if isinstance(path, str) and path.startswith("synthetic://"):      # roko_b200/synth.py: a seeded stand-in with the same schema
+        from . import synth
+        return synth
     try:
         import h5py
         return h5py
@@ -77,7 +80,7 @@ class InferenceDataset(Dataset):
             fd.close()
 
     def _open(self):
-        return (self._h5mod or _h5()).File(self.path, "r")
+        return (self._h5mod or _h5(self.path)).File(self.path, "r")
 
     def __getitem__(self, i):
         if self.fd is None:
@@ -336,7 +339,7 @@ class _SlabDataset(Dataset):
             fd.close()
 
     def _open(self):
-        return (self._h5mod or _h5()).File(self.path, "r")
+        return (self._h5mod or _h5(self.path)).File(self.path, "r")
 
     def __len__(self):
         return len(self.items)
@@ -348,6 +351,22 @@ class _SlabDataset(Dataset):
         grp = self.fd[g]
         x = torch.from_numpy(np.ascontiguousarray(grp["examples"][a:b])) if self.examples else torch.empty(0)
         return grp.attrs["contig"], torch.from_numpy(np.ascontiguousarray(grp["positions"][a:b])), x, flat
+
+    def read_into(self, i, x_out):
+        """Item i with its windows read STRAIGHT into ``x_out[:n]`` (a pinned staging tensor): ``Dataset.read_direct`` where the
+        backend has it (h5py, the synthetic file) -- no intermediate array, no page-faulting allocation per slab -- else a copy.
+        Returns (contig, positions, n, flat index of the first window)."""
+        if self.fd is None:
+            self.fd = self._open()
+        g, a, b, flat = self.items[i]
+        grp = self.fd[g]
+        ex, n = grp["examples"], b - a
+        dest = x_out.numpy()[:n]
+        if hasattr(ex, "read_direct"):
+            ex.read_direct(dest, np.s_[a:b])
+        else:
+            dest[...] = ex[a:b]
+        return grp.attrs["contig"], torch.from_numpy(np.ascontiguousarray(grp["positions"][a:b])), n, flat
 
 
 def _dist_env():
@@ -395,9 +414,11 @@ def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device
     meta = _SlabDataset(data, chunk, h5=h5, examples=False)                # full index (positions only)
     lo, hi = (0, meta.total) if world == 1 else rdist.shard_range(meta.total, rank, world)
     dataset = _SlabDataset(data, chunk, h5=h5, lo=lo, hi=hi)
-    loader = DataLoader(dataset, batch_size=None, shuffle=False, num_workers=workers)
-    x_pin = torch.empty((chunk, 200, 90), dtype=torch.uint8).pin_memory()
-    y_pin = torch.empty((chunk, 90), dtype=torch.uint8).pin_memory()
+    # two pinned staging buffers: while the model path (a blocking C call that releases the GIL) runs on one from a worker thread,
+    # the next slab is read straight into the other
+    from concurrent.futures import ThreadPoolExecutor
+    x_pin = [torch.empty((chunk, 200, 90), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    y_pin = [torch.empty((chunk, 90), dtype=torch.uint8).pin_memory() for _ in range(2)]
     votes = DenseVoteTable(device, budget_bytes=vote_budget) if rank == 0 else None
     remaining = {}                                                        # items still to vote per contig (rank 0)
     for g, a, b, _ in meta.items:
@@ -421,20 +442,43 @@ def infer_fast(data, model_path, out, workers=0, batch_size=128, h5=None, device
     local = torch.empty((hi - lo, 90), dtype=torch.uint8, device=device) if world > 1 else None
     done = 0
     lap("index")
-    for contig, pos, x, flat in loader:
-        n = x.shape[0]
-        x_pin[:n].copy_(x)
-        lap("read + stage")
-        model.predict_host(x_pin[:n], batch=batch_size, out=y_pin[:n], device=device)
-        lap("model path (H2D, kernels, D2H)")
+
+    def run_model(slot, n):
+        torch.cuda.set_device(device)
+        model.predict_host(x_pin[slot][:n], batch=batch_size, out=y_pin[slot][:n], device=device)
+
+    def finish(job):
+        """Wait for the model call of a staged slab, then hand its labels to the gather buffer / the vote."""
+        fut, slot, contig, pos, n, flat = job
+        fut.result()
+        lap("model path (H2D, kernels, D2H) not hidden behind reads")
         if world > 1:
-            local[flat - lo:flat - lo + n].copy_(y_pin[:n])
+            local[flat - lo:flat - lo + n].copy_(y_pin[slot][:n])
         else:
-            vote(contig, pos, y_pin[:n])
+            vote(contig, pos, y_pin[slot][:n])
             lap("vote + stitch")
-        done += n
-        if rank == 0 and (done // batch_size) % 100 == 0:
-            print(f"{done // batch_size} batches processed")
+
+    loader = iter(DataLoader(dataset, batch_size=None, shuffle=False, num_workers=workers)) if workers else None
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = None
+        for i in range(len(dataset)):
+            slot = i & 1                                                  # the other slot may still be in flight (pending)
+            if loader is None:
+                contig, pos, n, flat = dataset.read_into(i, x_pin[slot])
+            else:                                                         # worker processes read; one copy into pinned memory here
+                contig, pos, x, flat = next(loader)
+                n = x.shape[0]
+                x_pin[slot][:n].copy_(x)
+            lap("read + stage")
+            job = (pool.submit(run_model, slot, n), slot, contig, pos, n, flat)
+            if pending is not None:
+                finish(pending)
+            pending = job
+            done += n
+            if rank == 0 and (done // batch_size) % 100 == 0:
+                print(f"{done // batch_size} batches processed")
+        if pending is not None:
+            finish(pending)
     model.check_codes()                                                   # nn.Embedding would have raised on a bad code
     if world > 1:
         labels = rdist.gather_labels(local, meta.total)                   # (N, 90) uint8 on rank 0, rank order = file order

@@ -46,9 +46,16 @@ _BLOCK_CACHE = {}
 
 
 class _LazyRows:
-    def __init__(self, n, make):
-        self.n, self.make = n, make
+    def __init__(self, n, make, make_into=None):
+        self.n, self.make, self.make_into = n, make, make_into
         self.shape = (n,)
+        if make_into is not None:
+            self.read_direct = self._read_direct          # h5py.Dataset.read_direct(dest, source_sel): fill a caller-owned array
+
+    def _read_direct(self, dest, source_sel=None, dest_sel=None):
+        a, b, step = (source_sel if isinstance(source_sel, slice) else slice(None)).indices(self.n)
+        assert step == 1 and dest_sel is None
+        self.make_into(a, b, dest)
 
     def __len__(self):
         return self.n
@@ -90,6 +97,7 @@ class _File:
         self.contig_len = int(opts.get("contig_len", 3_000_000))
         self.group = int(opts.get("group", 3300))          # windows per group (a 100 kb region holds ~3 300)
         self.cache = int(opts.get("cache", 0))
+        self.labels = int(opts.get("labels", 0))           # labelled (training) file: every group also has ``labels`` (n, 90) int64 in 0..4
         per_contig = max(1, (self.contig_len - 90) // self.WINDOW_STEP)
         self._root = {"contigs": _SynGroup({})}
         first, ci = 0, 0
@@ -104,7 +112,10 @@ class _File:
                 self._root[f"{name}_{g0}"] = _SynGroup(
                     {"contig": name, "size": gn},
                     positions=_LazyRows(gn, lambda a, b, w0=g0: self._positions(w0 + a, w0 + b)),
-                    examples=_LazyRows(gn, lambda a, b, w0=first + g0: self._examples(w0 + a, w0 + b)))
+                    examples=_LazyRows(gn, lambda a, b, w0=first + g0: self._examples(w0 + a, w0 + b),
+                                       lambda a, b, out, w0=first + g0: self._examples(w0 + a, w0 + b, out)))
+                if self.labels:
+                    self._root[f"{name}_{g0}"]["labels"] = _LazyRows(gn, lambda a, b, w0=first + g0: self._labels(w0 + a, w0 + b))
             first += cn
             ci += 1
 
@@ -113,12 +124,24 @@ class _File:
         start = (np.arange(a, b, dtype=np.int64) * self.WINDOW_STEP)[:, None] + np.arange(COLS, dtype=np.int64)[None, :]
         return np.stack([start, np.zeros_like(start)], axis=2)
 
-    def _examples(self, a, b):
-        out = np.empty((b - a, READS, COLS), dtype=np.uint8)
+    def _examples(self, a, b, out=None):
+        if out is None:
+            out = np.empty((b - a, READS, COLS), dtype=np.uint8)
         blk = 4096                                             # generated in seed-addressed blocks: any range is reproducible
         for k in range(a // blk, (b - 1) // blk + 1):
             lo, hi = max(a, k * blk), min(b, (k + 1) * blk)
             block = self._block(k, min(blk, self.n - k * blk))
+            out[lo - a:hi - a] = block[lo - k * blk:hi - k * blk]
+        return out
+
+    def _labels(self, a, b):
+        """Uniform labels 0..4 per (window, column), reproducible by range like the examples."""
+        out = np.empty((b - a, COLS), dtype=np.int64)
+        blk = 65536
+        for k in range(a // blk, (b - 1) // blk + 1):
+            lo, hi = max(a, k * blk), min(b, (k + 1) * blk)
+            rng = np.random.Generator(np.random.PCG64(self.seed * 7_000_003 + k))
+            block = rng.integers(0, 5, size=(min(blk, self.n - k * blk), COLS), dtype=np.int64)
             out[lo - a:hi - a] = block[lo - k * blk:hi - k * blk]
         return out
 

@@ -41,7 +41,10 @@ PATIENCE = 7
 RUNNING_ALPHA = 0.98          # ignite.metrics.RunningAverage default
 
 
-def _h5():
+def _h5(path=None):
+    if isinstance(path, str) and path.startswith("synthetic://"):      # roko_b200/synth.py: a seeded stand-in with the same schema
+        from . import synth
+        return synth
     try:
         import h5py
         return h5py
@@ -50,6 +53,8 @@ def _h5():
 
 
 def get_filenames(path):
+    if path.startswith("synthetic://"):
+        return [path]
     if os.path.isdir(path):
         return sorted(os.path.join(path, f) for f in os.listdir(path) if f.endswith(".hdf5"))
     return [path]
@@ -80,7 +85,7 @@ class TrainDataset(Dataset):
                 fd.close()
 
     def _open(self, name):
-        return (self._h5mod or _h5()).File(name, "r")
+        return (self._h5mod or _h5(name)).File(name, "r")
 
     def __getitem__(self, i):
         if self.fds is None:
@@ -100,7 +105,7 @@ class InMemoryTrainDataset(Dataset):
     def __init__(self, path, transform=None, h5=None):
         xs, ys = [], []
         for name in get_filenames(path):
-            fd = (h5 or _h5()).File(name, "r")
+            fd = (h5 or _h5(name)).File(name, "r")
             try:
                 for g in _data_groups(fd):
                     xs.append(np.asarray(fd[g]["examples"][:], dtype=np.uint8))
@@ -128,7 +133,10 @@ class SlabLoader:
     batch kept.  A staging buffer is rewritten only after the copy that last read it has completed (one CUDA
     event per buffer), so the host may run ahead of the device by a step without corrupting a batch."""
 
-    def __init__(self, ds, batch_size, shuffle=False, generator=None, device="cpu"):
+    def __init__(self, ds, batch_size, shuffle=False, generator=None, device="cpu", shard=None):
+        # shard = (rank, per_rank_batch): data-parallel training gathers ONLY this rank's windows [rank b, (rank + 1) b) of every
+        # global batch (all ranks walk the same permutation) and yields (x, y, global batch size)
+        self.shard = shard
         self.x = torch.from_numpy(np.ascontiguousarray(ds.X))
         self.y = torch.from_numpy(np.ascontiguousarray(ds.Y))
         self.batch_size, self.shuffle, self.generator = int(batch_size), shuffle, generator
@@ -147,6 +155,10 @@ class SlabLoader:
         order = torch.randperm(self.n, generator=self.generator) if self.shuffle else torch.arange(self.n)
         for k, lo in enumerate(range(0, self.n, self.batch_size)):
             idx = order[lo:lo + self.batch_size]
+            n_global = idx.numel()
+            if self.shard is not None:
+                rank, b = self.shard
+                idx = idx[min(rank * b, n_global):min((rank + 1) * b, n_global)]
             slot = k & 1
             bx, by = self.bufs[slot]
             m = idx.numel()
@@ -155,13 +167,13 @@ class SlabLoader:
             torch.index_select(self.x, 0, idx, out=bx[:m])
             torch.index_select(self.y, 0, idx, out=by[:m])
             if self.device.type != "cuda":
-                yield bx[:m].clone(), by[:m].clone()
+                yield (bx[:m].clone(), by[:m].clone()) + ((n_global,) if self.shard is not None else ())
                 continue
             dx = bx[:m].to(self.device, non_blocking=True)
             dy = by[:m].to(self.device, non_blocking=True)
             self.copied[slot] = torch.cuda.Event()
             self.copied[slot].record(torch.cuda.current_stream(self.device))
-            yield dx, dy
+            yield (dx, dy) + ((n_global,) if self.shard is not None else ())
 
 
 class EarlyStopping:
@@ -259,7 +271,8 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     device = torch.device(device)
     if mem:
-        train_dl = SlabLoader(train_ds, global_batch, shuffle=True, generator=gen, device=device)
+        train_dl = SlabLoader(train_ds, global_batch, shuffle=True, generator=gen, device=device,
+                              shard=(rank, batch_size) if world > 1 else None)
         val_dl = SlabLoader(val_ds, batch_size, device=device) if val_ds is not None else None
     if model is None:
         model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)          # raises without a B200: no CPU path
@@ -270,14 +283,21 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
     log(f"Device: {device}  ranks: {world}  train windows: {len(train_ds)}"
         + (f"  val windows: {len(val_ds)}" if val_ds is not None else ""))
 
-    history = {"train_loss": [], "val_acc": [], "val_loss": [], "checkpoint": None, "epochs": 0}
+    history = {"train_loss": [], "val_acc": [], "val_loss": [], "checkpoint": None, "epochs": 0, "epoch_s": [], "epoch_windows": []}
+    import time
     running = None                       # ignite's RunningAverage, kept on the device: no host sync per step
     for epoch in range(1, epochs + 1):
-        for i, (x, y) in enumerate(train_dl, 1):
-            n_global = x.shape[0]
-            if world > 1:                                                   # this rank's windows of the global batch
-                lo, hi = min(rank * batch_size, n_global), min((rank + 1) * batch_size, n_global)
-                x, y = x[lo:hi], y[lo:hi]
+        t_epoch, seen = time.perf_counter(), 0
+        for i, item in enumerate(train_dl, 1):
+            x, y = item[0], item[1]
+            if len(item) == 3:                                              # the loader already took this rank's windows
+                n_global = item[2]
+            else:
+                n_global = x.shape[0]
+                if world > 1:                                               # this rank's windows of the global batch
+                    lo, hi = min(rank * batch_size, n_global), min((rank + 1) * batch_size, n_global)
+                    x, y = x[lo:hi], y[lo:hi]
+            seen += int(n_global)
             x = x.to(device, non_blocking=True)
             y = y.to(device, non_blocking=True).long()
             model.train()
@@ -295,8 +315,11 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
                 running = v.clone() if running is None else running.mul_(RUNNING_ALPHA).add_(v, alpha=1.0 - RUNNING_ALPHA)
             if i % 100 == 0:
                 log(f"ITERATION {i}/{len(train_dl)} - loss: {float(running) if running is not None else None}")
-        history["train_loss"].append(float(running) if running is not None else None)
+        history["train_loss"].append(float(running) if running is not None else None)   # (the float() synchronises the device)
         history["epochs"] = epoch
+        history["epoch_s"].append(time.perf_counter() - t_epoch)
+        history["epoch_windows"].append(seen)
+        log(f"Epoch {epoch}: {seen} windows in {history['epoch_s'][-1]:.2f} s = {seen / history['epoch_s'][-1]:,.0f} windows/s over {world} GPU(s)")
         if hasattr(model, "check_codes"):
             model.check_codes()              # nn.Embedding would have raised IndexError on a code outside 0..11
         if val_dl is None:
@@ -330,12 +353,17 @@ def main(argv=None):
     parser.add_argument("--memory", action="store_true", default=False)
     parser.add_argument("--t", type=int, default=0)
     parser.add_argument("--b", type=int, default=BATCH_SIZE)
+    parser.add_argument("--epochs", type=int, default=EPOCHS, help="(addition) stop after this many epochs; the reference runs 100 with early stopping")
     args = parser.parse_args(argv)
     if "RANK" in os.environ and "WORLD_SIZE" in os.environ:                # launched by torchrun: one process per GPU
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
-    train(args.train, args.out, args.val, args.memory, args.t, args.b)
+    hist = train(args.train, args.out, args.val, args.memory, args.t, args.b, epochs=args.epochs)
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return hist
 
 
 if __name__ == "__main__":

@@ -23,3 +23,18 @@ def test_synthetic_file_schema_and_reproducibility():
     assert ds.total == 9000 and sum(b - a for _, a, b, _ in ds.items) == 9000
     c, p, xs, flat = ds[len(ds) - 1]
     assert xs.shape[0] == p.shape[0] and flat + xs.shape[0] == 9000
+
+
+def test_read_direct_and_read_into_match_slicing():
+    import torch
+    path = "synthetic://5000?contig_len=90000&group=800&seed=3"
+    ds = inf._SlabDataset(path, 300, h5=synth, lo=450, hi=4100)
+    buf = torch.zeros((300, 200, 90), dtype=torch.uint8)
+    flat_expected = 450
+    for i in range(len(ds)):
+        c, p, x, flat = ds[i]
+        c2, p2, n, flat2 = ds.read_into(i, buf)
+        assert (c, flat, n) == (c2, flat2, x.shape[0]) and flat == flat_expected
+        assert torch.equal(buf[:n], x) and torch.equal(p, p2)
+        flat_expected += n
+    assert flat_expected == 4100

@@ -87,7 +87,7 @@ int roko_b200_infer_host(roko_b200_model* m, const uint8_t* x_host, long long n_
  *   "graphs"        replay the 8-kernel chain of roko_b200_forward_u8 as a CUDA graph (default 1; needs a non-default stream)
  *   "superbatch"    windows per device pass of roko_b200_infer_host (default 2368)
  * The fp16-split kernels scale their operands by powers of two (weights x 256, activations x 16 / x 256); a GRU weight
- * with |w| >= 253 or a front-end activation >= 4062 leaves their range: roko_b200_model_check then returns
+ * with |w| >= 253 or a front-end activation >= 4062 (fc1 or fc2 output) leaves their range: roko_b200_model_check then returns
  * ROKO_B200_ERANGE and the tf32 kernels ("proj" 3, "rec" 1) serve such a model. */
 int roko_b200_model_set_option(roko_b200_model* m, const char* name, long long value);
 

@@ -113,8 +113,8 @@ __host__ __device__ constexpr int pk_wh16(int l) {
 constexpr int RH16_W = 3 * 2 * HID * (HID / 2);  // 49 152 words
 constexpr int RH16_DIR = RH16_W + HID;
 __host__ __device__ constexpr int pk_rh16(int l, int d) { return pk_wh16(LAYERS) + (l * 2 + d) * RH16_DIR; }
-// fp16-split operands of the tcgen05 front end (front_tc.cu); scales: W1, E, M x 16; a, W2 x 256
-//   FT_W1HI  [128 rows j][104 words: r = 2c, 2c+1]   W1[j][r] x 16, hi halves -- tensor-memory image (rows >= 100 zero)
+// fp16-split operands of the tcgen05 front end (front_tc.cu); scales: W1 x 64, E and M x 4 (so a x 16), W2 x 256
+//   FT_W1HI  [128 rows j][104 words: r = 2c, 2c+1]   W1[j][r] x 64, hi halves -- tensor-memory image (rows >= 100 zero)
 //   FT_W1LO  [7 k atoms of 32 r][128 rows j][64 B]   lo halves, K-major SWIZZLE_64B shared-memory image (r < 208 used)
 //   FT_W2    [2 k atoms of 64 j][32 rows: hi of k = row, lo of k = row - 16][128 B]   W2[k][j] x 256, column j = 100 holds b2[k] x 256, SWIZZLE_128B
 constexpr int FT_K1 = 208;                       // read axis padded to 13 k steps of 16

@@ -38,8 +38,12 @@ constexpr int FT_PAIRS = COLS / 2;               // 45 column pairs per window
 constexpr int FT_N1 = 48;                        // MMA1 N: 4 columns x 12 codes
 constexpr int FT_N2 = 112;                       // MMA2 N: fc1 width 100 + bias-one row 100, padded to 16
 constexpr int FT_KSTEPS1 = FT_K1 / 16;           // 13
-constexpr float FT_S16 = 16.f;                   // scale of W1, E, M
-constexpr float FT_INV3 = 1.f / 65536.f;         // D3 = 256 (a) x 256 (W2) x g
+// power-of-two operand scales (fp16 range management, undone exactly): W1 x 64, M x 4, E x 4  =>  D2 = 16 a;  W2 x 256  =>  D3 = 4 096 g.
+// Headroom: |W1| < 1 000, |M| < 16 000, |E| < 16 000, a < 4 094 (beyond that roko_b200_model_check reports ROKO_B200_ERANGE
+// through the NaN / range test of the projection's producers, and `front` 0 -- the fp32-operand round-1 kernel -- serves the model).
+constexpr float FT_SW1 = 64.f, FT_SM = 4.f, FT_SE = 4.f;
+constexpr float FT_M_RESCALE = FT_SM / FT_SW1;   // D1 = 64 M  ->  M image = 4 M
+constexpr float FT_INV3 = 1.f / (FT_SE * FT_SM * 256.f);
 
 // tensor-memory columns (every accumulator starts at a multiple of 16)
 constexpr int FT_T_EHI = 0, FT_T_ELO = 16, FT_T_D3 = 32, FT_T_D1 = 64, FT_T_D2 = 160, FT_T_W1 = 384;
@@ -78,7 +82,7 @@ __host__ __device__ constexpr uint32_t sw64_off(uint32_t row, uint32_t chunk) {
                    "r"((v)[7]), "r"((v)[8]), "r"((v)[9]), "r"((v)[10]), "r"((v)[11]), "r"((v)[12]), "r"((v)[13]),        \
                    "r"((v)[14]), "r"((v)[15]) : "memory")
 
-// relu(D2) -> fp16 hi / lo words for two adjacent j (D2 is already 256 a: scales 16 x 16)
+// relu(D2) -> fp16 hi / lo words for two adjacent j (D2 is already 16 a: scales 4 x 4)
 __device__ __forceinline__ void relu_split2(uint32_t d0, uint32_t d1, uint32_t& hi, uint32_t& lo) {
     relu_split_f16x2(__uint_as_float(d0), __uint_as_float(d1), hi, lo);
 }
@@ -145,7 +149,7 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
             for (int t = 0; t < 2; ++t) {
                 const int k = 2 * wd + t, pp = k >> 4, c = k & 15;
                 float val = 0.f;
-                if (pp == pl && e < EMB) val = c < NCODES ? FT_S16 * __ldg(packed + PK_E + c * EMB + e) : (c == NCODES ? FT_S16 : 0.f);
+                if (pp == pl && e < EMB) val = c < NCODES ? FT_SE * __ldg(packed + PK_E + c * EMB + e) : (c == NCODES ? FT_SE : 0.f);
                 v2[t] = val;
             }
             split_f16x2(v2[0], v2[1], eh[wd], el[wd]);
@@ -164,8 +168,8 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
         // ================================ M converters: D1 -> fp16 hi/lo B operand of MMA2 =====================
         const int j = warp * 32 + lane;                                // row of M == TMEM lane of D1
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        // slot 12 of every column: b1[j] x 16 (row 100: the constant one that turns column 100 of a into 1)
-        const float bias = j < FC1 ? FT_S16 * __ldg(packed + PK_B1 + j) : (j == FC1 ? FT_S16 : 0.f);
+        // slot 12 of every column: b1[j] x 4 (row 100: the constant one that turns column 100 of a into 1)
+        const float bias = j < FC1 ? FT_SM * __ldg(packed + PK_B1 + j) : (j == FC1 ? FT_SM : 0.f);
         uint32_t bh, bl;
         split_f16x2(bias, 0.f, bh, bl);
         const uint32_t roff[4] = {sw64_off(j, 0), sw64_off(j, 1), sw64_off(j, 2), sw64_off(j, 3)};
@@ -189,12 +193,13 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
                     for (int pl = 0; pl < 2; ++pl) {
                         const uint32_t* m = v + pl * 12;
                         uint4 &h0 = hi[2 * pl], &l0 = lo[2 * pl], &h1 = hi[2 * pl + 1], &l1 = lo[2 * pl + 1];
-                        split_f16x2(__uint_as_float(m[0]), __uint_as_float(m[1]), h0.x, l0.x);
-                        split_f16x2(__uint_as_float(m[2]), __uint_as_float(m[3]), h0.y, l0.y);
-                        split_f16x2(__uint_as_float(m[4]), __uint_as_float(m[5]), h0.z, l0.z);
-                        split_f16x2(__uint_as_float(m[6]), __uint_as_float(m[7]), h0.w, l0.w);
-                        split_f16x2(__uint_as_float(m[8]), __uint_as_float(m[9]), h1.x, l1.x);
-                        split_f16x2(__uint_as_float(m[10]), __uint_as_float(m[11]), h1.y, l1.y);
+                        auto mv = [&](int i) { return __uint_as_float(m[i]) * FT_M_RESCALE; };
+                        split_f16x2(mv(0), mv(1), h0.x, l0.x);
+                        split_f16x2(mv(2), mv(3), h0.y, l0.y);
+                        split_f16x2(mv(4), mv(5), h0.z, l0.z);
+                        split_f16x2(mv(6), mv(7), h0.w, l0.w);
+                        split_f16x2(mv(8), mv(9), h1.x, l1.x);
+                        split_f16x2(mv(10), mv(11), h1.y, l1.y);
                         h1.z = bh; l1.z = bl; h1.w = 0u; l1.w = 0u;
                     }
                     mbar_wait(BAR(B_MEMPTY + gb), ((gg >> 1) & 1) ^ 1);   // MMA2 of pair gg - 2 has consumed this image

@@ -59,7 +59,7 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p, 
             const __half b = lo ? __float2half_rn(v1 - __half2float(h1)) : h1;
             return __uint_as_float((uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16));
         };
-        if (p >= PK_FT_W1HI) {                         // front_tc.cu operands (scales: W1 x 16, W2 x 256)
+        if (p >= PK_FT_W1HI) {                         // front_tc.cu operands (scales: W1 x 64, W2 x 256)
             auto pair_s = [&](float v0, float v1, float scale, bool lo) -> float {
                 v0 *= scale; v1 *= scale;
                 if (fabsf(v0) > 65000.f || fabsf(v1) > 65000.f) atomicOr(status, 2);
@@ -71,7 +71,7 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p, 
             auto w1 = [&](int j, int r) { return (j < FC1 && r < READS) ? raw[RAW_W1 + j * READS + r] : 0.f; };
             if (p < PK_FT_W1LO) {                      // [j][word c]: r = 2c, 2c+1, hi halves
                 const int i = p - PK_FT_W1HI, j = i / (FT_K1 / 2), c = i % (FT_K1 / 2);
-                return pair_s(w1(j, 2 * c), w1(j, 2 * c + 1), 16.f, false);
+                return pair_s(w1(j, 2 * c), w1(j, 2 * c + 1), 64.f, false);
             }
             if (p < PK_FT_W2) {                        // [k atom][row j][64 B], SWIZZLE_64B: chunk position = chunk ^ ((row >> 1) & 3)
                 const int ob = (p - PK_FT_W1LO) * 4;
@@ -79,7 +79,7 @@ __device__ __forceinline__ float pack_one(const float* __restrict__ raw, int p, 
                 const int j = (within / 512) * 8 + (within % 512) / 64;
                 const int pchunk = (within % 64) / 16, w4 = (within % 16) / 4;
                 const int r = atom * 32 + ((pchunk ^ ((j >> 1) & 3)) * 8) + w4 * 2;
-                return pair_s(w1(j, r), w1(j, r + 1), 16.f, true);
+                return pair_s(w1(j, r), w1(j, r + 1), 64.f, true);
             }
             {                                          // W2: [k atom of 64 j][32 rows: hi of k = row (0..15), lo of k = row - 16][128 B], SWIZZLE_128B; j = 100 carries b2
                 const int ob = (p - PK_FT_W2) * 4;

@@ -231,3 +231,21 @@ def test_fp16_range_guard(make_model, golden, seed1_state):
     m.predict(_dev(golden["x"][:1]))
     with pytest.raises(RokoB200Error):
         m.check_codes()
+
+
+def test_large_front_end_activations(make_model, seed1_state, golden):
+    """Trained models have larger fc1 outputs than a random initialisation: with the embedding scaled x80 (fc1 outputs of
+    several hundred) the fp16-split front end (operand scales chosen for a < 4 094) still agrees with the fp32-operand round-1 kernels."""
+    sd = {k: v.clone() for k, v in seed1_state.items()}
+    sd["embedding.weight"] *= 80.0
+    a, b = make_model(), make_model(front=0, proj=0, rec_tc_min=0)
+    a.load_state_dict(sd)
+    b.load_state_dict(sd)
+    x = _dev(golden["x"])
+    ta, tb = a.forward_taps(x), b.forward_taps(x)
+    scale = float(tb["front"].abs().max())
+    print("max front activation", scale)
+    assert scale > 50.0
+    assert float((ta["front"] - tb["front"]).abs().max()) <= 2e-6 * scale
+    assert float((ta["logits"] - tb["logits"]).abs().max()) <= TOL
+    a.check_codes()

@@ -13,12 +13,14 @@
 //     48 MMAs per step instead of rec_tc's 144;
 //   * W_hi (fp16, 3 x [128 x 128]) lives in TENSOR MEMORY as the A operand (192 columns), W_lo in shared memory
 //     (96 KB, K-major swizzled, one bulk copy per CTA lifetime); D = 3 gates x 64 columns;
-//   * the r and z gate tiles are multiplied and committed first, so the 512 gate threads run the two sigmoids
-//     (3 of the 5 MUFU operations per unit and window; r and z share one reciprocal) while the n tile multiplies.
+//   * the gate tiles are multiplied in the order r, n, z and committed one by one, so the 512 gate threads run r's sigmoid under
+//     the n tile's MMAs and the tanh (which needs r) under the z tile's; only z's sigmoid and the state update follow the last
+//     MMA.  (Round-2 trace, scripts/ubench/rec_trace.cu: with r and z first and n last, 1.35 k cycles of gate math trailed the
+//     last MMA of every 3.9 k-cycle step.)
 // Gate threads: thread = (hidden unit j = TMEM lane, 8 windows).  They read their unit's pre-activations with
 // tcgen05.ld, add the two partial columns, keep h in registers, write the layer output (fp32) and the scaled fp16
 // hi / lo split of h into the K-major swizzled H image for the next step.
-// mbarriers:  h_ready (512 gate threads -> MMA warp),  d_rz / d_n (tcgen05.commit -> gate threads),  w (W_lo landed).
+// mbarriers:  h_ready (512 gate threads -> MMA warp),  d_r / d_n / d_z (tcgen05.commit -> gate threads),  w (W_lo landed).
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -53,8 +55,8 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
     unsigned char* s_wlo = smem;
     unsigned char* s_h = smem + RH_WLO_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + RH_H_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    const uint32_t bar_h = smem_u32(bars), bar_rz = bar_h + 8, bar_n = bar_h + 16, bar_w = bar_h + 24;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const uint32_t bar_h = smem_u32(bars), bar_r = bar_h + 8, bar_n = bar_h + 16, bar_z = bar_h + 24, bar_w = bar_h + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.x & 1;
@@ -62,8 +64,9 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
 
     if (tid == 0) {
         mbar_init(bar_h, RH_GATE_THREADS);
-        mbar_init(bar_rz, 1);
+        mbar_init(bar_r, 1);
         mbar_init(bar_n, 1);
+        mbar_init(bar_z, 1);
         mbar_init(bar_w, 1);
         mbar_init_fence();
     }
@@ -140,28 +143,23 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
             mbar_arrive(bar_h);                                     // H = 0 is in place
 #pragma unroll 1
             for (int s = 0; s < COLS; ++s) {
-                uint32_t a0[RH_WPT], a1[RH_WPT], b0[RH_WPT], b1[RH_WPT];
-                mbar_wait(bar_rz, ph);
+                // The gate tiles arrive in the order r, n, z, each committed on its own: r's sigmoid runs under the n tile's MMAs,
+                // tanh (which needs r) under the z tile's MMAs, and only z's sigmoid + the state update remain after the last MMA.
+                uint32_t a0[RH_WPT], a1[RH_WPT];
+                mbar_wait(bar_r, ph);
                 tc_fence_after();
                 if (tid == 0) RTRACE(0, s);
                 ROKO_TMEM_LD8(a0, t_lane);                          // r: hi.hi + lo.hi
                 ROKO_TMEM_LD8(a1, t_lane + RH_N);                   // r: hi.lo
-                ROKO_TMEM_LD8(b0, t_lane + 2 * RH_N);               // z
-                ROKO_TMEM_LD8(b1, t_lane + 3 * RH_N);
                 tmem_wait_ld();
-                float rr[RH_WPT], zz[RH_WPT];                       // r, z while the n-gate MMAs are still running
+                float rr[RH_WPT], nn[RH_WPT];
 #pragma unroll
                 for (int b = 0; b < RH_WPT; ++b) {
-                    // r and z share one reciprocal: 1 / ((1 + ea)(1 + eb)); inputs clamped so the product stays finite
-                    const float xr = fmaxf(fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, g_r[b]), -40.f);
-                    const float xz = fmaxf(fmaf(__uint_as_float(b0[b]) + __uint_as_float(b1[b]), RH_INV, g_z[b]), -40.f);
-                    const float ea = 1.f + ex2f(-1.4426950408889634f * xr);
-                    const float eb = 1.f + ex2f(-1.4426950408889634f * xz);
-                    const float rc = rcpf(ea * eb);
-                    rr[b] = rc * eb; zz[b] = rc * ea;
+                    const float xr = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, g_r[b]);
+                    rr[b] = rcpf(1.f + ex2f(-1.4426950408889634f * xr));
                 }
                 if (tid == 0) RTRACE(1, s);
-                mbar_wait(bar_n, ph); ph ^= 1;
+                mbar_wait(bar_n, ph);
                 tc_fence_after();
                 if (tid == 0) RTRACE(2, s);
                 ROKO_TMEM_LD8(a0, t_lane + 4 * RH_N);               // n
@@ -170,8 +168,18 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
 #pragma unroll
                 for (int b = 0; b < RH_WPT; ++b) {
                     const float xn = fmaf(rr[b], fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, bhn), g_n[b]);
-                    const float n = fmaf(2.f, rcpf(1.f + ex2f(-2.8853900817779268f * xn)), -1.f);
-                    const float h = fmaf(zz[b], hprev[b] - n, n);
+                    nn[b] = fmaf(2.f, rcpf(1.f + ex2f(-2.8853900817779268f * xn)), -1.f);
+                }
+                mbar_wait(bar_z, ph); ph ^= 1;
+                tc_fence_after();
+                ROKO_TMEM_LD8(a0, t_lane + 2 * RH_N);               // z
+                ROKO_TMEM_LD8(a1, t_lane + 3 * RH_N);
+                tmem_wait_ld();
+#pragma unroll
+                for (int b = 0; b < RH_WPT; ++b) {
+                    const float xz = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, g_z[b]);
+                    const float z = rcpf(1.f + ex2f(-1.4426950408889634f * xz));
+                    const float h = fmaf(z, hprev[b] - nn[b], nn[b]);
                     hprev[b] = h;
                     unsigned short hi, lo;
                     split_f16(h * H_SCALE, hi, lo);
@@ -208,19 +216,17 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 tc_fence_after();
                 if (lane == 0) RTRACE(4, s);
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {              // r, z tiles first, committed on their own
+                for (int part = 0; part < 3; ++part) {              // gate tiles in the order r, n, z, each committed on its own
+                    const int mt = part == 0 ? 0 : (part == 1 ? 2 : 1);
+                    const uint32_t d = RH_D0 + mt * (2 * RH_N);
 #pragma unroll
-                    for (int mt = part ? 2 : 0; mt < (part ? 3 : 2); ++mt) {
-                        const uint32_t d = RH_D0 + mt * (2 * RH_N);
-#pragma unroll
-                        for (int kk = 0; kk < HID / 16; ++kk) {
-                            const uint64_t db = desc_sw128(b_img + (uint32_t)(kk >> 2) * (2 * RH_N * 128) + (uint32_t)(kk & 3) * 32);
-                            const uint64_t da = desc_sw128(a_lo + (uint32_t)mt * 32768 + (uint32_t)(kk >> 2) * 16384 + (uint32_t)(kk & 3) * 32);
-                            mma_f16_ts(d, RH_A_HI + mt * (HID / 2) + kk * 8, db, RH_ID64, kk ? 1u : 0u, elected);   // W_hi . [h_hi ; h_lo]
-                            mma_f16_ss(d, da, db, RH_ID32, 1u, elected);                                            // W_lo . h_hi  -> columns 0..31
-                        }
+                    for (int kk = 0; kk < HID / 16; ++kk) {
+                        const uint64_t db = desc_sw128(b_img + (uint32_t)(kk >> 2) * (2 * RH_N * 128) + (uint32_t)(kk & 3) * 32);
+                        const uint64_t da = desc_sw128(a_lo + (uint32_t)mt * 32768 + (uint32_t)(kk >> 2) * 16384 + (uint32_t)(kk & 3) * 32);
+                        mma_f16_ts(d, RH_A_HI + mt * (HID / 2) + kk * 8, db, RH_ID64, kk ? 1u : 0u, elected);   // W_hi . [h_hi ; h_lo]
+                        mma_f16_ss(d, da, db, RH_ID32, 1u, elected);                                            // W_lo . h_hi  -> columns 0..31
                     }
-                    mma_commit(part ? bar_n : bar_rz, elected);
+                    mma_commit(part == 0 ? bar_r : (part == 1 ? bar_n : bar_z), elected);
                 }
                 if (lane == 0) RTRACE(5, s);
                 __syncwarp();

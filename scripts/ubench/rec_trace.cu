@@ -1,6 +1,6 @@
 // Timeline probe for the tensor-core recurrence (rec_h.cu): clock64 stamps of CTA 0 for steps 20..23.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DROKO_TRACE -o scripts/ubench/rec_trace scripts/ubench/rec_trace.cu
-// slots per step: 0 gate thread 0: r/z tiles ready   1 r, z sigmoids done   2 n tile ready   3 h written + arrived
+// slots per step: 0 gate thread 0: r tile ready   1 r sigmoid done   2 n tile ready   3 h written + arrived
 //                 4 MMA warp: h ready, issue starts  5 MMA warp: 48 MMAs issued + both commits
 // (the ping-pong variant this probe was first written for lives in git history: commit df7c646, rec_h2_kernel)
 #include <stdio.h>
@@ -24,7 +24,7 @@ int main() {
     const long long t0 = t[4];
     for (int s = 0; s < 4; ++s) {
         const long long* p = t + s * 8;
-        printf("step %d: mma issue-start %6lld issue-end %6lld | gates rz-ready %6lld rz-done %6lld n-ready %6lld arrived %6lld\n",
+        printf("step %d: mma issue-start %6lld issue-end %6lld | gates r-ready %6lld r-done %6lld n-ready %6lld arrived %6lld\n",
                20 + s, p[4] - t0, p[5] - t0, p[0] - t0, p[1] - t0, p[2] - t0, p[3] - t0);
     }
     return 0;

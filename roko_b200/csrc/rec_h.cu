@@ -19,8 +19,10 @@
 //     last MMA of every 3.9 k-cycle step.)
 // Gate threads: thread = (hidden unit j = TMEM lane, 8 windows).  They read their unit's pre-activations with
 // tcgen05.ld, add the two partial columns, keep h in registers, write the layer output (fp32) and the scaled fp16
-// hi / lo split of h into the K-major swizzled H image for the next step.
-// mbarriers:  h_ready (512 gate threads -> MMA warp),  d_r / d_n / d_z (tcgen05.commit -> gate threads),  w (W_lo landed).
+// hi / lo split of h into the K-major swizzled H image for the next step.  The input projections gi of a step (32 windows x 384
+// floats) are staged into shared memory by a loader warp with one TMA bulk copy per window, two steps ahead.
+// mbarriers:  h_ready (512 gate threads -> MMA warp),  d_r / d_n / d_z (tcgen05.commit -> gate threads),  w (W_lo landed),
+//             gi_full / gi_empty per stage (loader warp <-> gate threads).
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -38,12 +40,15 @@ __device__ long long roko_trace[4096];
 constexpr int RH_N = 32;                         // windows per CTA pass
 constexpr int RH_GATE_THREADS = 512;             // 16 warps: TMEM lane quarter = warp & 3, window octet = warp >> 2
 constexpr int RH_WPT = RH_N / 4;                 // windows per gate thread (8)
-constexpr int RH_THREADS = RH_GATE_THREADS + 32;
+constexpr int RH_THREADS = RH_GATE_THREADS + 64;             // + MMA issuer warp + gi loader warp
 constexpr int RH_TMEM_COLS = 512;
 constexpr int RH_A_HI = 0, RH_D0 = 3 * (HID / 2);                // columns: W_hi 0..191, D 192..383 (gate tile mt at 192 + 64 mt)
 constexpr int RH_WLO_BYTES = G3 * HID * 2;                        // 98 304: [gate tile 3][k atom 2][128 rows][128 B]
 constexpr int RH_H_BYTES = 2 * (2 * RH_N) * 128;                  // 16 384: [k atom 2][64 rows: h_hi 0..31, h_lo 32..63][128 B]
-constexpr int RH_SMEM = RH_WLO_BYTES + RH_H_BYTES + 1024 /*align*/ + 64;
+constexpr int RH_GI_STAGES = 2;
+constexpr int RH_GI_BYTES = RH_N * G3 * 4;                        // 49 152: one step's gi of the CTA's 32 windows, [window][3 j + gate]
+constexpr int RH_SMEM = RH_WLO_BYTES + RH_H_BYTES + RH_GI_STAGES * RH_GI_BYTES + 1024 /*align*/ + 128;
+static_assert(RH_SMEM <= 232448, "shared memory budget");
 constexpr uint32_t RH_ID64 = idesc_f16(128, 2 * RH_N), RH_ID32 = idesc_f16(128, RH_N);
 constexpr float RH_INV = 1.f / (W_SCALE * H_SCALE);
 static_assert(RH_D0 + 3 * 2 * RH_N <= RH_TMEM_COLS, "tensor memory budget");
@@ -54,9 +59,11 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)rh_smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* s_wlo = smem;
     unsigned char* s_h = smem + RH_WLO_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_h + RH_H_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    unsigned char* s_gi = s_h + RH_H_BYTES;                         // [stage][window][384]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_gi + RH_GI_STAGES * RH_GI_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     const uint32_t bar_h = smem_u32(bars), bar_r = bar_h + 8, bar_n = bar_h + 16, bar_z = bar_h + 24, bar_w = bar_h + 32;
+    const uint32_t bar_gfull = bar_h + 40, bar_gempty = bar_h + 56;  // [stage]: gi landed (bulk-copy bytes) / gi consumed (512 gate threads)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.x & 1;
@@ -68,6 +75,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
         mbar_init(bar_n, 1);
         mbar_init(bar_z, 1);
         mbar_init(bar_w, 1);
+        for (int g = 0; g < RH_GI_STAGES; ++g) { mbar_init(bar_gfull + 8 * g, 1); mbar_init(bar_gempty + 8 * g, RH_GATE_THREADS); }
         mbar_init_fence();
     }
     if (warp == RH_GATE_THREADS / 32) tmem_alloc<RH_TMEM_COLS>(tmem_slot);
@@ -119,14 +127,14 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
         for (int b = 0; b < RH_WPT; ++b) hoff[b] = sw128_off((uint32_t)(oct * RH_WPT + b), (uint32_t)(j & 63));
         constexpr uint32_t LO_ROWS = (RH_N >> 3) * 1024;            // byte distance from row r to row r + 32 of the image
         const int dt = dir ? -1 : 1;
-        uint32_t ph = 0;
+        uint32_t ph = 0, gstep = 0;                                 // gstep: steps done by this CTA (all passes): stage = gstep % 2
         for (int pass = blockIdx.x >> 1; pass < npass; pass += gridDim.x >> 1) {
             const int t0 = dir ? COLS - 1 : 0;
             // one 32-bit element offset per window: out offset o = (w * 90 + t) * 256 + dir * 128 + j, and the gate-interleaved
             // gi layout makes its offset exactly 3 o  ((w * 90 + t) * 768 + dir * 384 + 3 j)
             unsigned oofs[RH_WPT];
             bool valid[RH_WPT];
-            float hprev[RH_WPT], g_r[RH_WPT], g_z[RH_WPT], g_n[RH_WPT];
+            float hprev[RH_WPT];
 #pragma unroll
             for (int b = 0; b < RH_WPT; ++b) {
                 const int w = pass * RH_N + oct * RH_WPT + b;
@@ -136,8 +144,6 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 hprev[b] = 0.f;
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(hs + hoff[b]), "h"((unsigned short)0) : "memory");
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(hs + hoff[b] + LO_ROWS), "h"((unsigned short)0) : "memory");
-                const float* gp = gi + 3u * oofs[b];
-                g_r[b] = __ldg(gp); g_z[b] = __ldg(gp + 1); g_n[b] = __ldg(gp + 2);
             }
             fence_async_smem();
             mbar_arrive(bar_h);                                     // H = 0 is in place
@@ -146,6 +152,10 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 // The gate tiles arrive in the order r, n, z, each committed on its own: r's sigmoid runs under the n tile's MMAs,
                 // tanh (which needs r) under the z tile's MMAs, and only z's sigmoid + the state update remain after the last MMA.
                 uint32_t a0[RH_WPT], a1[RH_WPT];
+                // this step's gi of my windows: staged by the loader warp (bulk copies, two steps ahead), [window][3 j + gate]
+                const uint32_t gstage = gstep % RH_GI_STAGES;
+                const float* gs = reinterpret_cast<const float*>(s_gi + gstage * RH_GI_BYTES) + (oct * RH_WPT) * G3 + j * 3;
+                mbar_wait(bar_gfull + 8 * gstage, (gstep / RH_GI_STAGES) & 1);
                 mbar_wait(bar_r, ph);
                 tc_fence_after();
                 if (tid == 0) RTRACE(0, s);
@@ -155,7 +165,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 float rr[RH_WPT], nn[RH_WPT];
 #pragma unroll
                 for (int b = 0; b < RH_WPT; ++b) {
-                    const float xr = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, g_r[b]);
+                    const float xr = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, gs[b * G3]);
                     rr[b] = rcpf(1.f + ex2f(-1.4426950408889634f * xr));
                 }
                 if (tid == 0) RTRACE(1, s);
@@ -167,7 +177,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 tmem_wait_ld();
 #pragma unroll
                 for (int b = 0; b < RH_WPT; ++b) {
-                    const float xn = fmaf(rr[b], fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, bhn), g_n[b]);
+                    const float xn = fmaf(rr[b], fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, bhn), gs[b * G3 + 2]);
                     nn[b] = fmaf(2.f, rcpf(1.f + ex2f(-2.8853900817779268f * xn)), -1.f);
                 }
                 mbar_wait(bar_z, ph); ph ^= 1;
@@ -177,7 +187,7 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 tmem_wait_ld();
 #pragma unroll
                 for (int b = 0; b < RH_WPT; ++b) {
-                    const float xz = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, g_z[b]);
+                    const float xz = fmaf(__uint_as_float(a0[b]) + __uint_as_float(a1[b]), RH_INV, gs[b * G3 + 1]);
                     const float z = rcpf(1.f + ex2f(-1.4426950408889634f * xz));
                     const float h = fmaf(z, hprev[b] - nn[b], nn[b]);
                     hprev[b] = h;
@@ -191,14 +201,28 @@ rec_h_kernel(const float* __restrict__ gi, const float* __restrict__ rh16_d0, fl
                 fence_async_smem();
                 mbar_arrive(bar_h);                                 // h_t is in shared memory, D has been consumed
                 if (tid == 0) RTRACE(3, s);
-                if (s + 1 < COLS) {                                 // lands while the tensor core runs the next step
+                mbar_arrive(bar_gempty + 8 * gstage);               // this stage of gi may be refilled
+                ++gstep;
 #pragma unroll
-                    for (int b = 0; b < RH_WPT; ++b) {
-                        oofs[b] += dt * OUT_W;
-                        const float* gp = gi + 3u * oofs[b];
-                        g_r[b] = __ldg(gp); g_z[b] = __ldg(gp + 1); g_n[b] = __ldg(gp + 2);
-                    }
-                }
+                for (int b = 0; b < RH_WPT; ++b) oofs[b] += dt * OUT_W;
+            }
+        }
+    } else if (warp == RH_GATE_THREADS / 32 + 1) {
+        // ================================ gi loader: one bulk copy per window and step ==============
+        // gi[w][t][dir * 384 ..] is 1 536 contiguous bytes; lane = window.  Two steps are in flight, so the gate threads never wait
+        // on HBM (with the one-step register prefetch this replaced, `long_scoreboard` was the top stall at full load).
+        uint32_t gstep = 0;
+        for (int pass = blockIdx.x >> 1; pass < npass; pass += gridDim.x >> 1) {
+            const int w = pass * RH_N + lane;
+            const int wl = w < nwin ? w : nwin - 1;                 // windows past the batch re-read the last one (never stored)
+            const int dt = dir ? -1 : 1;
+            const float* src = gi + ((size_t)wl * COLS + (dir ? COLS - 1 : 0)) * GI_N + dir * G3;
+            for (int s = 0; s < COLS; ++s, ++gstep, src += dt * GI_N) {
+                const uint32_t st = gstep % RH_GI_STAGES;
+                mbar_wait(bar_gempty + 8 * st, ((gstep / RH_GI_STAGES) & 1) ^ 1);
+                if (lane == 0) mbar_expect_tx(bar_gfull + 8 * st, RH_GI_BYTES);
+                __syncwarp();
+                bulk_g2s(smem_u32(s_gi) + st * RH_GI_BYTES + lane * (G3 * 4), src, G3 * 4, bar_gfull + 8 * st);
             }
         }
     } else {

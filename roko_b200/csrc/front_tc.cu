@@ -8,7 +8,7 @@
 // with a SIMT gather for M (7.2 MB of shared-memory reads per window) and warp-level mma.sync for a and g;
 // it is bound by shared-memory wavefronts and by the legacy MMA's issue cost, and the two do not overlap.
 // Here ALL THREE contractions run on the tensor cores as fp16-split MMAs with fp32 accumulation (tc.cuh):
-//   MMA1  D1[j][(p,c)]   = sum_r W1[j][r] . OneHot[(p,c)][r]         M=128 (j), N=48 (4 columns x 12 codes), K=208
+//   MMA1  D1[j][(p,c)]   = sum_r W1[j][r] . OneHot[(p,c)][r]         M=128 (j), N=96 (8 columns x 12 codes), K=208
 //         the gather as a GEMM: the one-hot operand is exact in fp16 (so 2 terms: W1_hi, W1_lo), it is built by 4
 //         warps straight from the window bytes (12 x 16-byte stores per 8 reads), W1_hi lives in tensor memory
 //   MMA2  D2[(p,e)][j]   = sum_{(p',c)} Eblk[(p,e)][(p',c)] . M[j][(p',c)]      M=128 (2 columns x 64 e), N=112, K=32
@@ -33,9 +33,10 @@ namespace roko {
 using namespace tc;
 
 constexpr int FT_THREADS = 21 * 32;
-constexpr int FT_GROUPS = 23;                    // 4-column groups per window (the last one holds 2 columns)
+constexpr int FT_GROUPS = 12;                    // 8-column groups per window (the last one holds 2 columns)
+constexpr int FT_GP = 4;                         // column pairs per group
 constexpr int FT_PAIRS = COLS / 2;               // 45 column pairs per window
-constexpr int FT_N1 = 48;                        // MMA1 N: 4 columns x 12 codes
+constexpr int FT_N1 = 96;                        // MMA1 N: 8 columns x 12 codes (an MMA costs ~40-55 cycles from N = 32 to 96: twice the columns per instruction)
 constexpr int FT_N2 = 112;                       // MMA2 N: fc1 width 100 + bias-one row 100, padded to 16
 constexpr int FT_KSTEPS1 = FT_K1 / 16;           // 13
 // power-of-two operand scales (fp16 range management, undone exactly): W1 x 64, M x 4, E x 4  =>  D2 = 16 a;  W2 x 256  =>  D3 = 4 096 g.
@@ -47,11 +48,11 @@ constexpr float FT_INV3 = 1.f / (FT_SE * FT_SM * 256.f);
 
 // tensor-memory columns (every accumulator starts at a multiple of 16)
 constexpr int FT_T_EHI = 0, FT_T_ELO = 16, FT_T_D3 = 32, FT_T_D1 = 64, FT_T_D2 = 160, FT_T_W1 = 384;
-static_assert(FT_T_D3 + 32 == FT_T_D1 && FT_T_D1 + 2 * FT_N1 == FT_T_D2 && FT_T_D2 + 2 * FT_N2 == FT_T_W1 && FT_T_W1 + FT_K1 / 2 <= 512, "TMEM map");
+static_assert(FT_T_D3 + 32 == FT_T_D1 && FT_T_D1 + FT_N1 == FT_T_D2 && FT_T_D2 + 2 * FT_N2 == FT_T_W1 && FT_T_W1 + FT_K1 / 2 <= 512, "TMEM map");
 
 // shared memory (bytes, from a 1024-aligned base)
 constexpr int FT_S_W1LO = 0;                                   // 57 344  [7 atoms][128 rows][64 B]
-constexpr int FT_S_OH = FT_S_W1LO + 7 * 128 * 64;              // 2 x 21 504  [7 atoms][48 rows][64 B]
+constexpr int FT_S_OH = FT_S_W1LO + 7 * 128 * 64;              // 2 x 43 008  [7 atoms][96 rows][64 B]
 constexpr int FT_OH_BYTES = 7 * FT_N1 * 64;
 constexpr int FT_S_MIMG = FT_S_OH + 2 * FT_OH_BYTES;           // 2 x (hi 7 168 + lo 7 168)  [112 rows][64 B]
 constexpr int FT_MIMG_BYTES = FT_N2 * 64;
@@ -176,18 +177,22 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
         for (int it = 0; it < nmine; ++it) {
 #pragma unroll 1
             for (int h = 0; h < FT_GROUPS; ++h) {
-                const uint32_t hg = (uint32_t)it * FT_GROUPS + h, hb = hg & 1;
-                mbar_wait(BAR(B_D1FULL + hb), (hg >> 1) & 1);
+                const uint32_t hg = (uint32_t)it * FT_GROUPS + h;
+                mbar_wait(BAR(B_D1FULL), hg & 1);                       // D1 is single buffered
                 tc_fence_after();
-                const int npairs = h < FT_GROUPS - 1 ? 2 : 1;
+                const int npairs = h < FT_GROUPS - 1 ? FT_GP : 1;
                 for (int q = 0; q < npairs; ++q) {
-                    const uint32_t gg = (uint32_t)it * FT_PAIRS + 2 * h + q, gb = gg & 1;
+                    const uint32_t gg = (uint32_t)it * FT_PAIRS + FT_GP * h + q, gb = gg & 1;
                     uint32_t v[24];
-                    const uint32_t ta = lane_base + FT_T_D1 + hb * FT_N1 + q * 24;
+                    const uint32_t ta = lane_base + FT_T_D1 + q * 24;
                     ROKO_TMEM_LD8(v, ta);
                     ROKO_TMEM_LD8(v + 8, ta + 8);
                     ROKO_TMEM_LD8(v + 16, ta + 16);
                     tmem_wait_ld();
+                    if (q == npairs - 1) {                              // the group's last columns are in registers: D1 may be overwritten
+                        tc_fence_before();
+                        mbar_arrive(BAR(B_D1EMPTY));
+                    }
                     uint4 hi[4], lo[4];                                 // chunks: [p0 c0-7] [p0 c8-11, bias, 0] [p1 c0-7] [p1 c8-11, bias, 0]
 #pragma unroll
                     for (int pl = 0; pl < 2; ++pl) {
@@ -214,8 +219,6 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
                     fence_async_smem();
                     mbar_arrive(BAR(B_MFULL + gb));
                 }
-                tc_fence_before();
-                mbar_arrive(BAR(B_D1EMPTY + hb));                       // D1[hb] may be overwritten
             }
         }
     } else if (warp < 12) {
@@ -297,7 +300,6 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
     } else if (warp < 20) {
         // ================================ one-hot builders (+ window TMA) ======================================
         const int t = tid - 16 * 32;                                     // 0 .. 127
-        const int pl = t / 26, rc = t % 26;                              // task: column pl of the group, reads 8 rc .. 8 rc + 7 (t < 104)
         auto fetch_window = [&](int it_) {
             const int w_ = blockIdx.x + it_ * gridDim.x;
             mbar_expect_tx(BAR(B_XFULL + (it_ & 1)), WIN_BYTES);
@@ -308,43 +310,51 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
             if (nmine > 1) fetch_window(1);
         }
         bool bad = false;
-        // destination of my 16-byte chunk in row n = pl * 12 + c of an OH buffer: k atom rc >> 2, chunk rc & 3
-        uint32_t doff[NCODES];
-#pragma unroll
-        for (int c = 0; c < NCODES; ++c) doff[c] = (uint32_t)(rc >> 2) * (FT_N1 * 64) + sw64_off((uint32_t)(pl * NCODES + c), (uint32_t)(rc & 3));
+        // tasks of a group: (column pl of 8, read chunk rc of 26) = 208; thread t takes tasks t and t + 128
         for (int it = 0; it < nmine; ++it) {
             mbar_wait(BAR(B_XFULL + (it & 1)), (it >> 1) & 1);
             const unsigned char* xs = smem + FT_S_XS + (it & 1) * FT_XS_BYTES;
 #pragma unroll 1
             for (int h = 0; h < FT_GROUPS; ++h) {
                 const uint32_t hg = (uint32_t)it * FT_GROUPS + h, hb = hg & 1;
-                const int p = 4 * h + pl;
-                uint32_t c03 = 0xFFFFFFFFu, c47 = 0xFFFFFFFFu;           // my 8 codes, one per byte (0xFF = no read)
-                if (t < 104 && p < COLS) {
-                    uint32_t code[8];
+                uint32_t c03[2], c47[2];                                 // my 8 codes per task, one per byte (0xFF = no read)
+                bool live[2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * rc + i;
-                        code[i] = r < READS ? xs[r * COLS + p] : 255u;
-                        bad |= (r < READS && code[i] >= NCODES);
+                for (int k = 0; k < 2; ++k) {
+                    const int task = t + 128 * k, pl = task / 26, rc = task % 26, p = 8 * h + pl;
+                    live[k] = task < 208 && p < COLS;
+                    c03[k] = c47[k] = 0xFFFFFFFFu;
+                    if (live[k]) {
+                        uint32_t code[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 8 * rc + i;
+                            code[i] = r < READS ? xs[r * COLS + p] : 255u;
+                            bad |= (r < READS && code[i] >= NCODES);
+                        }
+                        c03[k] = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+                        c47[k] = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
                     }
-                    c03 = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
-                    c47 = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
                 }
                 mbar_wait(BAR(B_OHEMPTY + hb), ((hg >> 1) & 1) ^ 1);     // MMA1 of group hg - 2 has consumed this buffer
-                if (t < 104 && p < COLS) {
-                    unsigned char* oh = smem + FT_S_OH + hb * FT_OH_BYTES;
+                unsigned char* oh = smem + FT_S_OH + hb * FT_OH_BYTES;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!live[k]) continue;
+                    const int task = t + 128 * k, pl = task / 26, rc = task % 26;
+                    // my 16-byte chunk of row n = pl * 12 + c: k atom rc >> 2, chunk rc & 3
+                    unsigned char* base = oh + (uint32_t)(rc >> 2) * (FT_N1 * 64);
 #pragma unroll
                     for (int c = 0; c < NCODES; ++c) {
                         // byte-wise compare (0xFF where the read carries code c), bytes spread to the high byte of each half,
                         // masked to fp16 1.0 = 0x3C00
-                        const uint32_t m0 = __vcmpeq4(c03, 0x01010101u * (uint32_t)c), m1 = __vcmpeq4(c47, 0x01010101u * (uint32_t)c);
+                        const uint32_t m0 = __vcmpeq4(c03[k], 0x01010101u * (uint32_t)c), m1 = __vcmpeq4(c47[k], 0x01010101u * (uint32_t)c);
                         uint4 o;
                         o.x = __byte_perm(m0, 0u, 0x1404) & 0x3C003C00u;
                         o.y = __byte_perm(m0, 0u, 0x3424) & 0x3C003C00u;
                         o.z = __byte_perm(m1, 0u, 0x1404) & 0x3C003C00u;
                         o.w = __byte_perm(m1, 0u, 0x3424) & 0x3C003C00u;
-                        *reinterpret_cast<uint4*>(oh + doff[c]) = o;
+                        *reinterpret_cast<uint4*>(base + sw64_off((uint32_t)(pl * NCODES + c), (uint32_t)(rc & 3))) = o;
                     }
                 }
                 fence_async_smem();
@@ -363,19 +373,19 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
         const uint32_t elected = elect_one();
         mbar_wait(BAR(B_CONST), 0);                                      // W1_lo and W2 images have landed
         constexpr uint32_t ID1 = idesc_f16(128, FT_N1), ID2 = idesc_f16(128, FT_N2), ID3 = idesc_f16(128, 32), ID3L = idesc_f16(128, 16);
-        auto mma1 = [&](uint32_t hg) {                                   // D1[hb] = W1 . OneHot(group hg)
+        auto mma1 = [&](uint32_t hg) {                                   // D1 = W1 . OneHot(group hg)
             const uint32_t hb = hg & 1;
             mbar_wait(BAR(B_OHFULL + hb), (hg >> 1) & 1);
-            mbar_wait(BAR(B_D1EMPTY + hb), ((hg >> 1) & 1) ^ 1);
+            mbar_wait(BAR(B_D1EMPTY), (hg & 1) ^ 1);                     // the M converters hold the previous group's columns in registers
             tc_fence_after();
-            const uint32_t d = FT_T_D1 + hb * FT_N1, oh = sbase + FT_S_OH + hb * FT_OH_BYTES, wl = sbase + FT_S_W1LO;
+            const uint32_t d = FT_T_D1, oh = sbase + FT_S_OH + hb * FT_OH_BYTES, wl = sbase + FT_S_W1LO;
 #pragma unroll
             for (int kk = 0; kk < FT_KSTEPS1; ++kk) {
                 const uint64_t db = desc_sw64(oh + (kk >> 1) * (FT_N1 * 64) + (kk & 1) * 32);
                 mma_f16_ss(d, desc_sw64(wl + (kk >> 1) * (128 * 64) + (kk & 1) * 32), db, ID1, kk ? 1u : 0u, elected);   // W1_lo
                 mma_f16_ts(d, FT_T_W1 + kk * 8, db, ID1, 1u, elected);                                                    // W1_hi
             }
-            mma_commit(BAR(B_D1FULL + hb), elected);
+            mma_commit(BAR(B_D1FULL), elected);
             mma_commit(BAR(B_OHEMPTY + hb), elected);
             __syncwarp();
         };
@@ -416,12 +426,14 @@ front_tc_kernel(const uint8_t* __restrict__ x, const float* __restrict__ packed,
             mma1(h0);
 #pragma unroll 1
             for (int h = 0; h < FT_GROUPS; ++h) {
-                if (h + 1 < FT_GROUPS) mma1(h0 + h + 1);                 // next group's gather runs while this group's M is converted
-                const int npairs = h < FT_GROUPS - 1 ? 2 : 1;
+                const int npairs = h < FT_GROUPS - 1 ? FT_GP : 1;
                 for (int q = 0; q < npairs; ++q) {
-                    const uint32_t gg = g0 + 2 * h + q;
+                    const uint32_t gg = g0 + FT_GP * h + q;
                     mma2(gg);
-                    if (2 * h + q > 0) mma3(gg - 1);                     // a of the previous pair has been split meanwhile
+                    if (FT_GP * h + q > 0) mma3(gg - 1);                 // a of the previous pair has been split meanwhile
+                    // D1 is single buffered: the next group's gather is issued once this group's second pair is under way -- by
+                    // then the converters have read (or are about to read) the group's last columns out of D1
+                    if (q == 1 && h + 1 < FT_GROUPS) mma1(h0 + h + 1);
                 }
             }
             mma3(g0 + FT_PAIRS - 1);

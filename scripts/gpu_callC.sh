@@ -1,10 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 60 scripts/ubench/rec_trace
 DIAG_SIZES=128,2368 timeout 400 python scripts/gpu_diag.py "default:" > gpurun_out/cC_diag.log 2>&1
 echo "diag rc=$?"; cat gpurun_out/cC_diag.log | cut -c1-1300
 timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/cC_pytest.log 2>&1
 echo "pytest rc=$?"; tail -n 5 gpurun_out/cC_pytest.log
-ROKO_B200_REC_TC_MIN=32 ROKO_B200_GRAPHS=0 timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python scripts/profile_target.py 40 1 > gpurun_out/r02_memcheck_b40.log 2>&1
-echo "memcheck rc=$?"; tail -n 2 gpurun_out/r02_memcheck_b40.log

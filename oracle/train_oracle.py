@@ -29,21 +29,27 @@ def mask_shapes(batch):
 
 def kernel_keep_masks(p, seed, batch):
     """numpy restatement of the counter-based masks of roko_b200/csrc/train.cuh (drop_hash / drop_keep):
-    keep element i of site s  <=>  p == 0  or  hi32(splitmix64(i + (seed ^ (s+1) * K))) >= floor(p * 2^32)."""
+    (k1, k2) = hi32, lo32 of splitmix64(seed ^ (s+1) * K);  keep element i of site s  <=>  p == 0  or
+    lowbias32(i + k1) ^ k2 >= floor(p * 2^32)   (32-bit multiply-xorshift finaliser, arithmetic mod 2^32)."""
     out = {}
-    thresh = np.uint64(int(p * 4294967296.0))
+    thresh = np.uint32(int(p * 4294967296.0))
     with np.errstate(over="ignore"):
         for site, (name, shape) in enumerate(mask_shapes(batch).items()):
             n = int(np.prod(shape))
             if thresh == 0:
                 out[name] = np.ones(shape, dtype=np.uint8)
                 continue
-            z = np.arange(n, dtype=np.uint64) + (np.uint64(seed) ^ (np.uint64(site + 1) * np.uint64(0xD1B54A32D192ED03)))
+            z = np.uint64(seed) ^ (np.uint64(site + 1) * np.uint64(0xD1B54A32D192ED03))
             z = z + np.uint64(0x9E3779B97F4A7C15)
             z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
             z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
             z = z ^ (z >> np.uint64(31))
-            out[name] = ((z >> np.uint64(32)) >= thresh).astype(np.uint8).reshape(shape)
+            k1, k2 = np.uint32(z >> np.uint64(32)), np.uint32(z & np.uint64(0xFFFFFFFF))
+            x = np.arange(n, dtype=np.uint64).astype(np.uint32) + k1
+            x = (x ^ (x >> np.uint32(16))) * np.uint32(0x7FEB352D)
+            x = (x ^ (x >> np.uint32(15))) * np.uint32(0x846CA68B)
+            x = x ^ (x >> np.uint32(16))
+            out[name] = ((x ^ k2) >= thresh).astype(np.uint8).reshape(shape)
     return out
 
 

@@ -15,15 +15,18 @@ constexpr int PE = EMB * READS;           // 10 000 embedding outputs per (windo
 // The keep bits of the block's 10 000 outputs are filed as 313 words (MASK_WORDS per block) for the backward.
 __global__ void __launch_bounds__(TR_THREADS)
 embed_drop_kernel(const uint8_t* __restrict__ x, const float* __restrict__ E, float* __restrict__ ep,
-                  uint32_t* __restrict__ bits, DropCfg d, int* __restrict__ status) {
+                  uint32_t* __restrict__ bits, uint8_t* __restrict__ xt, uint32_t* __restrict__ bitsT, DropCfg d,
+                  int* __restrict__ status) {
     __shared__ float Es[NCODES * EMB];
     __shared__ uint8_t codes[READS];
+    __shared__ uint8_t kept[PE];                                        // keep flags, [channel][read], for the transposed file
     const int bp = blockIdx.x, b = bp / COLS, p = bp - b * COLS, tid = threadIdx.x;
     for (int i = tid; i < NCODES * EMB; i += TR_THREADS) Es[i] = E[i];
     if (tid < READS) {
         uint8_t c = x[((size_t)b * READS + tid) * COLS + p];
         if (c >= NCODES) { atomicOr(status, 1); c = 0; }
         codes[tid] = c;
+        if (xt) xt[(size_t)bp * READS + tid] = c;
     }
     __syncthreads();
     float* dst = ep + (size_t)bp * PE;
@@ -35,10 +38,20 @@ embed_drop_kernel(const uint8_t* __restrict__ x, const float* __restrict__ E, fl
             const float v = Es[codes[r] * EMB + e];
             const unsigned long long i0 = (((unsigned long long)b * READS + r) * COLS + p) * EMB + e;
             keep = drop_keep(d, DROP_EMB, i0);
-            dst[idx] = keep ? v * d.scale : 0.f;
+            if (ep) dst[idx] = keep ? v * d.scale : 0.f;
+            kept[idx] = keep;
         }
         const uint32_t word = __ballot_sync(0xffffffffu, keep);
         if ((tid & 31) == 0) bdst[idx >> 5] = word;
+    }
+    if (bitsT) {
+        __syncthreads();
+        if (tid < READS) {
+            unsigned long long w = 0ull;
+#pragma unroll 10
+            for (int e = 0; e < EMB; ++e) w |= (unsigned long long)kept[e * READS + tid] << e;
+            reinterpret_cast<uint2*>(bitsT)[(size_t)bp * READS + tid] = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+        }
     }
 }
 
@@ -280,10 +293,10 @@ static int grid_for(size_t n, int cap) {
     return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
 }
 
-cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, int nwin, DropCfg d,
-                              int* status, cudaStream_t s) {
+cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, uint8_t* xt, uint32_t* bitsT, int nwin,
+                              DropCfg d, int* status, cudaStream_t s) {
     if (nwin <= 0) return cudaSuccess;
-    embed_drop_kernel<<<nwin * COLS, TR_THREADS, 0, s>>>(x, E, ep, bits, d, status);
+    embed_drop_kernel<<<nwin * COLS, TR_THREADS, 0, s>>>(x, E, ep, bits, xt, bitsT, d, status);
     return cudaGetLastError();
 }
 

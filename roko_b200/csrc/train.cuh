@@ -20,13 +20,20 @@ struct DropCfg {
 
 __host__ __device__ __forceinline__ unsigned int drop_hash(unsigned long long seed, unsigned int site,
                                                            unsigned long long idx) {
-    // splitmix64 finaliser over (seed, site, idx)
-    unsigned long long z = idx + (seed ^ ((unsigned long long)(site + 1) * 0xD1B54A32D192ED03ull));
+    // stream keys (k1, k2): splitmix64 finaliser of (seed, site) -- uniform per launch, hoisted out of every loop
+    unsigned long long z = seed ^ ((unsigned long long)(site + 1) * 0xD1B54A32D192ED03ull);
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    return (unsigned int)(z >> 32);
+    // per element: a 32-bit multiply-xorshift finaliser of (idx + k1), whitened with k2.  32-bit arithmetic only (9
+    // instructions against ~45 for a 64-bit splitmix per element, which made the fc1 epilogue and the embedding pass
+    // hash-bound); element indices are < 2^32 for every site up to the 1024-window batch limit.
+    unsigned int x = (unsigned int)idx + (unsigned int)(z >> 32);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x ^ (unsigned int)z;
 }
 __host__ __device__ __forceinline__ bool drop_keep(const DropCfg& d, unsigned int site, unsigned long long idx) {
     return d.thresh == 0u || drop_hash(d.seed, site, idx) >= d.thresh;
@@ -46,9 +53,12 @@ cudaError_t launch_gemm(GemmArgs g, bool ka, bool kb, int epi, int splits, int n
 cudaError_t gemm_setup();
 
 // ---- element-wise / small kernels (train.cu) -----------------------------------------------------
+constexpr int MASKT_WORDS = 2 * READS;   // transposed keep bits of one (window, column): 64 bits (50 used) per read
 constexpr int MASK_WORDS = 320;          // keep bits of one (window, column)'s 10 000 embedding outputs (313 words used)
-cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, int nwin, DropCfg d,
-                              int* status, cudaStream_t s);
+// ep may be NULL (keep bits and codes only); xt [nwin*90][200] receives the validated codes of each (window, column) and
+// bitsT [nwin*90][200][2] the keep bits transposed (per read, bit = channel), or NULL
+cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint32_t* bits, uint8_t* xt, uint32_t* bitsT, int nwin,
+                              DropCfg d, int* status, cudaStream_t s);
 cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, float* u, int rows50, DropCfg d,
                            cudaStream_t s);
 cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2,
@@ -62,6 +72,17 @@ cudaError_t launch_gru_bias_grad(const float* dgi, const float* dghn, int rows, 
 cudaError_t launch_drop_mask(unsigned int site, size_t n, uint8_t* out, DropCfg d, cudaStream_t s);
 
 // ---- row-streaming front-end products on tcgen05 (train_tc.cu) -------------------------------------
+// The masked embedding ep[(bp, e)][r] = keep ? E[xt[bp][r]][e] * scale : 0 takes 600 distinct values per seed: instead of
+// storing its 0.46 GB per 128 windows, the products that consume it rebuild their operand tiles from the codes (1 byte per
+// 50 values) and the keep bits (bit e*200 + r of the (window, column)'s MASK_WORDS words).
+struct EpGen {
+    const uint8_t* xt;
+    const uint32_t* bits;
+    const uint32_t* bitsT;   // the same keep bits filed per read: [window*90 + column][200][2 words], bit e of the pair
+    const float* E;          // [12][50] embedding table (fp32, as loaded)
+    float scale;             // 1 / (1 - p)
+    float* dE;               // embedding gradient [12][50] (fused d(ep) product only)
+};
 size_t train_tc_image_floats();
 cudaError_t train_tc_setup();
 cudaError_t launch_train_images(const float* raw, float* img, cudaStream_t s);
@@ -72,6 +93,10 @@ cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, fl
                           int num_sms, cudaStream_t s);
 cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s);
 cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s);
+// the same three products with ep regenerated from (codes, keep bits); the d(ep) product reduces straight into dE
+cudaError_t launch_fc1_gen(EpGen gen, const float* img, const float* b1, float* a1, int rows, DropCfg d, int num_sms, cudaStream_t s);
+cudaError_t launch_dw1_gen(const float* dap, EpGen gen, float* dW1, int rows, int num_sms, cudaStream_t s);
+cudaError_t launch_dep_de(const float* dap, const float* img, EpGen gen, int rows, int num_sms, cudaStream_t s);
 
 // ---- recurrence (rec.cu forward with gate saving, rec_bwd.cu) -------------------------------------
 // gates: [row][dir][j] float4 (r, z, n, W_hn h + b_hn)

@@ -30,11 +30,13 @@ constexpr int TRAIN_MAX_WINDOWS = 1024;
 constexpr size_t ROW_EP = (size_t)EMB * READS;       // per (window, column) row
 constexpr size_t ROW_A1 = (size_t)EMB * FC1;
 constexpr size_t ROW_FLOATS = ROW_EP + ROW_A1 + IN0P + GI_N + 3 * (2 * HID * 4) + 3 * OUT_W + 2 * OUT_W
-                              + GI_N + OUT_W + OUT_W + IN0P + MASK_WORDS;
+                              + GI_N + OUT_W + OUT_W + IN0P + MASK_WORDS + MASKT_WORDS + READS / 4;
 
 struct TrainWs {
     float *ep, *a1, *u, *gi, *gates[3], *out[3], *outd[2], *dghp, *dghn, *dh, *din;
     uint32_t* bits;
+    uint32_t* bitsT;                 // keep bits per read, [row][200][2]
+    uint8_t* xt;                     // validated codes, [row][200]
 };
 
 TrainWs carve(void* base, size_t rows) {
@@ -51,7 +53,9 @@ TrainWs carve(void* base, size_t rows) {
     w.dghn = p; p += rows * OUT_W;
     w.dh = p; p += rows * OUT_W;
     w.din = p; p += rows * IN0P;
-    w.bits = reinterpret_cast<uint32_t*>(p);
+    w.bits = reinterpret_cast<uint32_t*>(p); p += rows * MASK_WORDS;
+    w.bitsT = reinterpret_cast<uint32_t*>(p); p += rows * MASKT_WORDS;
+    w.xt = reinterpret_cast<uint8_t*>(p);
     return w;
 }
 
@@ -102,10 +106,13 @@ int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows,
     const float* pk = m->packed;
 
     TCU(cudaMemsetAsync(w.u, 0, (size_t)rows * IN0P * sizeof(float), s));      // the 12 pad columns stay zero
-    TCU(launch_embed_drop(x, raw + RAW_E, w.ep, w.bits, n_windows, d, m->status, s));
+    const bool gen_ep = m->train_tc >= 5;                 // ep is rebuilt inside its consumers from (codes, keep bits), never stored
+    const EpGen gen{w.xt, w.bits, w.bitsT, raw + RAW_E, d.scale, nullptr};
+    TCU(launch_embed_drop(x, raw + RAW_E, gen_ep ? nullptr : w.ep, w.bits, w.xt, gen_ep ? w.bitsT : nullptr, n_windows, d, m->status, s));
     if (m->train_tc) {   // a1 = dropout(relu(ep W1^T + b1))                     rnn_model.py:50-51
         TCU(launch_train_images(raw, m->train_img, s));
-        TCU(launch_fc1_tc(w.ep, m->train_img, raw + RAW_B1, w.a1, rows50, d, m->num_sms, s));
+        if (gen_ep) TCU(launch_fc1_gen(gen, m->train_img, raw + RAW_B1, w.a1, rows50, d, m->num_sms, s));
+        else TCU(launch_fc1_tc(w.ep, m->train_img, raw + RAW_B1, w.a1, rows50, d, m->num_sms, s));
     } else {
         GemmArgs a{};
         a.A = w.ep; a.lda = READS; a.B = raw + RAW_W1; a.ldb = READS; a.C = w.a1; a.ldc = FC1;
@@ -160,7 +167,7 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         TCU(launch_rec_bwd(w.dh, reinterpret_cast<const float4*>(w.gates[l]), w.out[l], raw + raw_whh(l, 0),
                            (size_t)raw_dir_size(l), dgi, w.dghn, w.dghp, n_windows, sms, s));
         for (int dir = 0; dir < 2; ++dir) {
-            if (m->train_tc >= 4) {                       // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
+            if (m->train_tc == 4) {                       // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
                 TCU(launch_tn_tc(dgi + dir * G3, GI_N, G3, in, in_ld, in_w, grad_raw + raw_wih(l, dir), in_w, rows, 256, sms, s));
                 TCU(launch_tn_tc(w.dghp + dir * G3, GI_N, G3, w.out[l] + dir * HID, OUT_W, HID, grad_raw + raw_whh(l, dir), HID,
                                  rows, 128, sms, s));
@@ -193,7 +200,11 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
     // front end: fc2, fc1, embedding
     TCU(launch_fc2_bwd(w.din, w.u, w.a1, raw + RAW_W2, grad_raw + RAW_W2, grad_raw + RAW_B2, rows50, d.scale, sms, s));
     {
-        if (m->train_tc >= 2) {                           // dW1 = dap^T ep
+        const bool gen_ep = m->train_tc >= 5;
+        const EpGen gen{w.xt, w.bits, w.bitsT, raw + RAW_E, d.scale, grad_raw + RAW_E};
+        if (gen_ep) {                                     // dW1 = dap^T ep, ep rebuilt from (codes, keep bits)
+            TCU(launch_dw1_gen(w.a1, gen, grad_raw + RAW_W1, rows50, sms, s));
+        } else if (m->train_tc >= 2) {                    // dW1 = dap^T ep
             TCU(launch_dw1_tc(w.a1, w.ep, grad_raw + RAW_W1, rows50, sms, s));
         } else {
             GemmArgs a{};
@@ -202,6 +213,10 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
             TCU(launch_gemm(a, false, false, EPI_ATOMIC, 0, sms, s));
         }
         TCU(launch_colsum(w.a1, FC1, rows50, FC1, grad_raw + RAW_B1, s));
+        if (gen_ep) {                                     // dE straight from the d(ep) = dap W1 tiles
+            TCU(launch_dep_de(w.a1, m->train_img, gen, rows50, sms, s));
+            return ROKO_B200_OK;
+        }
         if (m->train_tc) {                                // dep = dap W1 (over ep, which nothing reads any more)
             TCU(launch_dep_tc(w.a1, m->train_img, w.ep, rows50, sms, s));
         } else {

@@ -15,7 +15,7 @@ constexpr int T_THREADS = 320;
 constexpr int T_BM = 128, T_BK = 32;
 constexpr int T_A_IMG = T_BM * T_BK * 4;               // 16 KB
 constexpr int T_EPI_ROW = 36;
-constexpr int T_EPI_BYTES = 4 * 32 * T_EPI_ROW * 4;
+constexpr int T_EPI_BYTES = 26 * 1024;                 // store epilogues: 4 x 32 x 36 floats; d(ep) epilogue: 24 KB of bins + staged codes
 __host__ __device__ constexpr int t_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
 __host__ __device__ constexpr int t_stages(int bn) { return bn <= 128 ? 3 : 2; }     // what fits 227 KB
 __host__ __device__ constexpr int t_smem_bytes(int bn) { return t_stages(bn) * t_stage_bytes(bn) + 1024 + 256 + T_EPI_BYTES; }
@@ -69,17 +69,35 @@ __device__ __forceinline__ float t_tf32_hi(float v) {
     return __uint_as_float(u);
 }
 
-enum { TEPI_STORE = 0, TEPI_FC1 = 1 };
+__device__ __forceinline__ float t_lds(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void t_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+
+enum { TEPI_STORE = 0, TEPI_FC1 = 1, TEPI_DE = 2 };
+constexpr int EP_VALUES = NCODES * EMB;                // the embedding table, 600 floats
+constexpr int DE_SETS = 4;                             // independent bin sets of the TEPI_DE epilogue (column r uses set r & 3)
+constexpr int DE_CROW = 208;                           // staged codes: bytes per (window, column) row (200 used)
 
 // C[m][0..NREAL) (row stride LDC) = epilogue(A[m][0..KREAL) (row stride LDA) x W), W as NT x KB pairs of
 // hi / lo images of BN rows x 32 floats ([n tile][k block][hi | lo]); image rows beyond NREAL and columns
 // beyond KREAL are zero.  Output tile t covers rows (t / NT) * 128.., columns (t % NT) * BN...
-template <int BN, int KB, int NT, int LDA, int KREAL, int NREAL, int LDC, int EPI>
+//
+// AGEN = 1: A is the masked embedding ep (rows = (window, column, channel), k = read), rebuilt from gen's codes and keep
+// bits instead of loaded.  EPI = TEPI_DE: the output tile is d(ep); instead of storing it, every row adds its kept
+// columns into 12 per-code bins (shared memory, one column of bins per thread) -> dE[code][channel of the row].
+template <int BN, int KB, int NT, int LDA, int KREAL, int NREAL, int LDC, int EPI, int AGEN = 0>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, const float* __restrict__ bias,
-                 float* __restrict__ C, int M, int ntiles, DropCfg drop) {
+                 float* __restrict__ C, int M, int ntiles, DropCfg drop, const EpGen gen) {
     static_assert(KREAL % 4 == 0 && NREAL % 4 == 0 && LDA % 4 == 0 && LDC % 4 == 0 && KB * T_BK >= KREAL && NT * BN >= NREAL
                   && 2 * BN <= 512 && (EPI != 1 || NT == 1), "shape");
+    static_assert(!AGEN || (KREAL == READS && LDA == READS), "generated A is the masked embedding");
+    static_assert(EPI != TEPI_DE || (NREAL == READS && NT == 1 && DE_SETS * NCODES * 128 * 4 + 2 * 4 * DE_CROW <= T_EPI_BYTES), "d(ep) epilogue");
+    static_assert(4 * 32 * T_EPI_ROW * 4 <= T_EPI_BYTES, "store epilogue staging");
+    __shared__ float Es[AGEN ? EP_VALUES : 1];             // E * scale
     constexpr int W_IMG = BN * T_BK * 4;
     constexpr int STAGE = t_stage_bytes(BN);
     constexpr int NS = t_stages(BN);                       // operand pipeline depth
@@ -112,12 +130,86 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if constexpr (AGEN) for (int i = tid; i < EP_VALUES; i += T_THREADS) Es[i] = gen.E[i] * gen.scale;
+    if constexpr (EPI == TEPI_DE)
+        for (int i = tid; i < DE_SETS * NCODES * 128; i += T_THREADS) epi_stage[i] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp < 4) {
+    if (AGEN && warp < 4) {
+        // ------------------------------- A producers, operand rebuilt from codes + keep bits ----------
+        // thread = 4 consecutive reads (chunk) of rows rr + 16 i; per k block and row one word of codes and one nibble of bits
+        const int chunk = tid & 7, rr = tid >> 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = (tile / NT) * T_BM;
+            const uint8_t* crow[8];
+            const uint32_t* brow[8];
+            int ev[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + rr + 16 * i;
+                const bool valid = m < M;
+                const int bp = valid ? m / EMB : 0;
+                ev[i] = valid ? m - bp * EMB : -1;
+                crow[i] = gen.xt + (size_t)bp * READS + chunk * 4;
+                brow[i] = gen.bits + (size_t)bp * MASK_WORDS;
+            }
+            uint32_t cw[2][8], kn[2][8];
+            auto load_block = [&](uint32_t (&c)[8], uint32_t (&k)[8], int kb) {
+                const int k0 = kb * T_BK + chunk * 4;
+                const bool kin = k0 < KREAL;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    c[i] = 0u; k[i] = 0u;
+                    if (ev[i] >= 0 && kin) {
+                        const int idx = ev[i] * READS + k0;                 // multiple of 4: the nibble never straddles a word
+                        c[i] = __ldg(reinterpret_cast<const uint32_t*>(crow[i] + kb * T_BK));
+                        k[i] = (__ldg(brow[i] + (idx >> 5)) >> (idx & 31)) & 15u;
+                    }
+                }
+            };
+            auto store_block = [&](const uint32_t (&c)[8], const uint32_t (&k)[8]) {
+                const int s = it % NS;
+                t_mbar_wait(BAR(B_EM + s), ((it / NS) & 1) ^ 1);
+                unsigned char* ahi = smem + s * STAGE;
+                unsigned char* alo = ahi + T_A_IMG;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rr + 16 * i;
+                    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+                    const int e = ev[i] < 0 ? 0 : ev[i];
+                    float4 v, h, l;
+                    v.x = (k[i] & 1u) ? Es[(c[i] & 255u) * EMB + e] : 0.f;
+                    v.y = (k[i] & 2u) ? Es[((c[i] >> 8) & 255u) * EMB + e] : 0.f;
+                    v.z = (k[i] & 4u) ? Es[((c[i] >> 16) & 255u) * EMB + e] : 0.f;
+                    v.w = (k[i] & 8u) ? Es[(c[i] >> 24) * EMB + e] : 0.f;
+                    h.x = t_tf32_hi(v.x); l.x = v.x - h.x;
+                    h.y = t_tf32_hi(v.y); l.y = v.y - h.y;
+                    h.z = t_tf32_hi(v.z); l.z = v.z - h.z;
+                    h.w = t_tf32_hi(v.w); l.w = v.w - h.w;
+                    *reinterpret_cast<float4*>(ahi + off) = h;
+                    *reinterpret_cast<float4*>(alo + off) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                t_mbar_arrive(BAR(s));
+                ++it;
+            };
+            load_block(cw[0], kn[0], 0);
+            if (KB > 1) load_block(cw[1], kn[1], 1);
+#pragma unroll 1
+            for (int kb = 0; kb < KB; kb += 2) {
+                store_block(cw[0], kn[0]);
+                if (kb + 2 < KB) load_block(cw[0], kn[0], kb + 2);
+                if (kb + 1 < KB) {
+                    store_block(cw[1], kn[1]);
+                    if (kb + 3 < KB) load_block(cw[1], kn[1], kb + 3);
+                }
+            }
+        }
+    } else if (warp < 4) {
         // ------------------------------- A producers ----------------------------------------------
         // two k blocks of loads in flight per thread (registers), NS blocks in shared memory
         const int chunk = tid & 7, rr = tid >> 3;
@@ -219,6 +311,132 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
             if (elected) t_umma_commit(BAR(B_AF + buf));
             __syncwarp();
         }
+    } else if (EPI == TEPI_DE) {
+        // ------------------------------- epilogue warps (6..9): d(ep) tile -> per-code sums ---------
+        // thread = row (one channel e of one (window, column)); column r of the tile belongs to code xt[bp][r] and counts
+        // when its keep bit is set.  Bins [set][code][thread] in shared memory: a thread only ever adds into its own column
+        // of bins (bank = lane); column r uses set r & 3, so four read-modify-write chains are in flight at a time.
+        // After a tile, thread t gathers the bins of targets T = t + 128 k (T = code * 50 + channel; the <= 3 rows of the
+        // tile with that channel) into registers that live for the whole kernel -- no shared-memory atomics -- and clears
+        // them.  The next tile's keep bits (8 words per row) and codes (the <= 4 (window, column)s a tile spans, staged
+        // in shared memory) are fetched while the current tile is processed.
+        const int q = warp & 3, tl = q * 32 + lane;
+        const uint32_t bins0 = t_smem_u32(epi_stage);                 // cell (set, code, row) at ((set * 12 + code) * 128 + row) * 4
+        const uint32_t mybins = bins0 + 4u * tl;
+        unsigned char* sc = reinterpret_cast<unsigned char*>(epi_stage + DE_SETS * NCODES * 128);     // [2][4][DE_CROW] codes
+        const int nbp = (M + EMB - 1) / EMB;
+        constexpr int NTGT = (EP_VALUES + 127) / 128;                 // 5 targets per thread
+        float tacc[NTGT];
+        int tch[NTGT];                                                // channel of the target, -1 = none
+        uint32_t tbin[NTGT];                                          // address of cell (set 0, code of the target, row 0)
+#pragma unroll
+        for (int k = 0; k < NTGT; ++k) {
+            const int T = tl + 128 * k, c = T / EMB;
+            tacc[k] = 0.f;
+            tch[k] = T < EP_VALUES ? T - c * EMB : -1;
+            tbin[k] = bins0 + 4u * (c * 128);
+        }
+        uint32_t Wn[8];
+        uint2 cpre = make_uint2(0u, 0u);
+        auto prefetch = [&](int tile) {
+            const int m = tile * T_BM + tl;
+            const bool valid = tile < ntiles && m < M;
+            const int bp = valid ? m / EMB : 0, e = valid ? m - bp * EMB : 0;
+            const uint32_t* bw = gen.bits + (size_t)bp * MASK_WORDS + ((e * READS) >> 5);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Wn[k] = valid ? __ldg(bw + k) : 0u;
+            const int bpq = tl / 26, off = tl - bpq * 26, sbp = (tile * T_BM) / EMB + bpq;      // 4 rows of 26 x 8 bytes
+            cpre = make_uint2(0u, 0u);
+            if (tile < ntiles && bpq < 4 && off < READS / 8 && sbp < nbp)
+                cpre = __ldg(reinterpret_cast<const uint2*>(gen.xt + (size_t)sbp * READS) + off);
+        };
+        prefetch(blockIdx.x);
+        int j = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+            const uint32_t buf = j & 1;
+            const int m = tile * T_BM + tl;
+            const bool valid = m < M;
+            const int bp = valid ? m / EMB : 0, e = valid ? m - bp * EMB : 0;
+            const int bpl = valid ? bp - (tile * T_BM) / EMB : 0;
+            const uint32_t sh = (uint32_t)(e * READS) & 31u;
+            uint32_t W[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) W[k] = Wn[k];
+            unsigned char* scb = sc + buf * 4 * DE_CROW;
+            if (tl < 4 * 26) *reinterpret_cast<uint2*>(scb + (tl / 26) * DE_CROW + (tl % 26) * 8) = cpre;
+            asm volatile("bar.sync 1, 128;" ::: "memory");            // codes staged; the previous tile's gather is complete
+            prefetch(tile + gridDim.x);
+            const unsigned char* crow = scb + bpl * DE_CROW;
+            t_mbar_wait(BAR(B_AF + buf), (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll
+            for (int c = 0; c < (NREAL + 31) / 32; ++c) {
+                uint32_t r[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)(32 * c)));
+                const int ncol = NREAL - 32 * c < 32 ? NREAL - 32 * c : 32;          // 32, or 8 in the last group
+                uint32_t keep = __funnelshift_r(W[c], W[c + 1], sh);
+                if (ncol < 32) keep &= (1u << ncol) - 1u;
+                if (!valid) keep = 0u;
+                uint32_t cw[8];
+#pragma unroll
+                for (int w = 0; w < 8; w += 2) {
+                    if (4 * w < ncol) {
+                        const uint2 t2 = *reinterpret_cast<const uint2*>(crow + 32 * c + 4 * w);
+                        cw[w] = t2.x; cw[w + 1] = t2.y;
+                    } else { cw[w] = 0u; cw[w + 1] = 0u; }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (4 * g < ncol) {
+                        constexpr uint32_t SET = NCODES * 128 * 4;          // bytes per bin set
+                        const uint32_t a0 = mybins + ((cw[g] << 9) & 0x1FE00u);
+                        const uint32_t a1 = mybins + SET + ((cw[g] << 1) & 0x1FE00u);
+                        const uint32_t a2 = mybins + 2 * SET + ((cw[g] >> 7) & 0x1FE00u);
+                        const uint32_t a3 = mybins + 3 * SET + ((cw[g] >> 15) & 0x1FE00u);
+                        const float v0 = t_lds(a0), v1 = t_lds(a1), v2 = t_lds(a2), v3 = t_lds(a3);
+                        t_sts(a0, v0 + (((keep >> (4 * g)) & 1u) ? __uint_as_float(r[4 * g]) : 0.f));
+                        t_sts(a1, v1 + (((keep >> (4 * g + 1)) & 1u) ? __uint_as_float(r[4 * g + 1]) : 0.f));
+                        t_sts(a2, v2 + (((keep >> (4 * g + 2)) & 1u) ? __uint_as_float(r[4 * g + 2]) : 0.f));
+                        t_sts(a3, v3 + (((keep >> (4 * g + 3)) & 1u) ? __uint_as_float(r[4 * g + 3]) : 0.f));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            t_mbar_arrive(BAR(B_AE + buf));
+            asm volatile("bar.sync 2, 128;" ::: "memory");            // every row's bins are final
+            const int off50 = (tile * T_BM) % EMB;                   // channel of the tile's first row
+#pragma unroll
+            for (int k = 0; k < NTGT; ++k) {
+                if (tch[k] >= 0) {
+                    int row = tch[k] - off50;
+                    if (row < 0) row += EMB;
+#pragma unroll
+                    for (int rep = 0; rep < 3; ++rep, row += EMB) {
+                        if (row < T_BM) {
+#pragma unroll
+                            for (int st = 0; st < DE_SETS; ++st) {
+                                const uint32_t a = tbin[k] + 4u * row + st * (NCODES * 128 * 4);
+                                tacc[k] += t_lds(a);
+                                t_sts(a, 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NTGT; ++k)
+            if (tch[k] >= 0 && tacc[k] != 0.f) atomicAdd(gen.dE + tl + 128 * k, tacc[k] * gen.scale);
     } else {
         // ------------------------------- epilogue warps (6..9) -------------------------------------
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
@@ -298,14 +516,16 @@ struct TnArgs {
     const float* B; int ldb; int Nreal;
     float* C; int ldc;
     int rows;
+    EpGen gen;             // BGEN: B is the masked embedding (rows = (window, column, channel), 200 columns), rebuilt not loaded
 };
 constexpr int DW_THREADS = 288;                        // 8 producer warps (0-3 also epilogue) + 1 MMA warp
 __host__ __device__ constexpr int dw_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
 __host__ __device__ constexpr int dw_smem_bytes(int bn) { return 2 * dw_stage_bytes(bn) + 1024 + 256; }
 constexpr int DW_MAXT = 12;                            // tasks per producer warp: (128 + 256) / 4 quads over 8 warps
 
-template <int BN>
+template <int BN, int BGEN = 0>
 __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
+    __shared__ float Es[BGEN ? EP_VALUES : 1];             // E * scale
     constexpr int W_IMG = BN * T_BK * 4;
     constexpr int STAGE = dw_stage_bytes(BN);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
@@ -337,6 +557,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     // image rows the producers never write (beyond ma / nb) feed accumulator rows / columns nobody reads:
     // zero them once so they at least hold finite numbers
     for (int i = tid; i < 2 * STAGE / 16; i += DW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (BGEN) for (int i = tid; i < EP_VALUES; i += DW_THREADS) Es[i] = g.gen.E[i] * g.gen.scale;
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t_smem_u32(tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -347,7 +568,105 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp < 8) {
+    if (BGEN && warp < 8) {
+        // ------------------------------- producers, B = masked embedding rebuilt in place -----------
+        // Nothing to transpose on the B side: thread r (< 200) owns image row r = one read and computes its 32 values of
+        // the block (rows = consecutive channels of one or two (window, column)s) from the read's code(s) and the
+        // per-read keep words (bitsT) -> eight 16-byte stores per image.  The A side (dap, row-major [row][100]) is read
+        // as (column j, 4 consecutive rows): lanes = consecutive j, coalesced 4-byte loads, one 16-byte store per image.
+        // Everything that does not depend on the block is computed once; loads of block it + 1 are issued before block
+        // it is stored.
+        constexpr int NA = (FC1 * 8 + 255) / 256;                       // 4 A tasks per thread
+        int a_off[NA], a_k[NA];
+        const float* a_ptr[NA];
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            const int task = tid + 256 * u, kq = task / FC1, j = task - kq * FC1;
+            a_k[u] = task < FC1 * 8 ? 4 * kq : (1 << 28);              // out-of-range tasks fail every row test
+            a_off[u] = (j >> 3) * 1024 + (j & 7) * 128 + (((kq & 7) ^ (j & 7)) << 4);
+            a_ptr[u] = g.A + ((size_t)kb0 * T_BK + 4 * (kq & 7)) * FC1 + j;
+        }
+        const bool b_on = tid < READS;
+        const int r = b_on ? tid : 0;
+        const int b_off = 2 * T_A_IMG + (r >> 3) * 1024 + (r & 7) * 128;
+        const int nbp = g.rows / EMB;
+        struct Loads { float a[NA][4]; uint2 wA, wB; uint32_t cA, cB; };
+        auto load_block = [&](Loads& L, int it) {
+            const int k0 = (kb0 + it) * T_BK;
+#pragma unroll
+            for (int u = 0; u < NA; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    L.a[u][i] = (k0 + a_k[u] + i < g.rows) ? __ldg(a_ptr[u] + ((size_t)it * T_BK + i) * FC1) : 0.f;
+            const int bp0 = k0 / EMB;
+            L.wA = L.wB = make_uint2(0u, 0u);
+            L.cA = L.cB = 0u;
+            if (b_on && bp0 < nbp) {
+                L.wA = __ldg(reinterpret_cast<const uint2*>(g.gen.bitsT) + (size_t)bp0 * READS + r);
+                L.cA = __ldg(g.gen.xt + (size_t)bp0 * READS + r);
+            }
+            if (b_on && bp0 + 1 < nbp) {
+                L.wB = __ldg(reinterpret_cast<const uint2*>(g.gen.bitsT) + (size_t)(bp0 + 1) * READS + r);
+                L.cB = __ldg(g.gen.xt + (size_t)(bp0 + 1) * READS + r);
+            }
+        };
+        auto store_block = [&](const Loads& L, int it) {
+            const int s = it & 1, k0 = (kb0 + it) * T_BK;
+            t_mbar_wait(BAR(2 + s), ((it >> 1) & 1) ^ 1);
+            unsigned char* st = smem + s * STAGE;
+#pragma unroll
+            for (int u = 0; u < NA; ++u) {
+                if (a_k[u] < T_BK) {
+                    float4 h, l;
+                    h.x = t_tf32_hi(L.a[u][0]); l.x = L.a[u][0] - h.x;
+                    h.y = t_tf32_hi(L.a[u][1]); l.y = L.a[u][1] - h.y;
+                    h.z = t_tf32_hi(L.a[u][2]); l.z = L.a[u][2] - h.z;
+                    h.w = t_tf32_hi(L.a[u][3]); l.w = L.a[u][3] - h.w;
+                    *reinterpret_cast<float4*>(st + a_off[u]) = h;
+                    *reinterpret_cast<float4*>(st + T_A_IMG + a_off[u]) = l;
+                }
+            }
+            if (b_on) {
+                const int bp0 = k0 / EMB, e0 = k0 - bp0 * EMB;
+                const int n1 = EMB - e0;                                // rows of the block inside (window, column) bp0 (>= 32: all)
+                const unsigned long long mA = ((unsigned long long)L.wA.y << 32) | L.wA.x;
+                const unsigned long long mB = ((unsigned long long)L.wB.y << 32) | L.wB.x;
+                uint32_t keep = (uint32_t)(mA >> e0);                   // channels >= 50 hold zeros
+                if (n1 < T_BK) keep |= (uint32_t)mB << n1;
+                const int baseA = (int)L.cA * EMB + e0, baseB = (int)L.cB * EMB - n1;
+#pragma unroll
+                for (int kq = 0; kq < 8; ++kq) {
+                    float v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 4 * kq + i;
+                        v[i] = ((keep >> k) & 1u) ? Es[(k < n1 ? baseA : baseB) + k] : 0.f;
+                    }
+                    const int off = b_off + ((kq ^ (r & 7)) << 4);
+                    float4 h, l;
+                    h.x = t_tf32_hi(v[0]); l.x = v[0] - h.x;
+                    h.y = t_tf32_hi(v[1]); l.y = v[1] - h.y;
+                    h.z = t_tf32_hi(v[2]); l.z = v[2] - h.z;
+                    h.w = t_tf32_hi(v[3]); l.w = v[3] - h.w;
+                    *reinterpret_cast<float4*>(st + off) = h;
+                    *reinterpret_cast<float4*>(st + W_IMG + off) = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            t_mbar_arrive(BAR(s));
+        };
+        Loads L0, L1;
+        if (nkb > 0) load_block(L0, 0);
+#pragma unroll 1
+        for (int it = 0; it < nkb; it += 2) {
+            if (it + 1 < nkb) load_block(L1, it + 1);
+            store_block(L0, it);
+            if (it + 1 < nkb) {
+                if (it + 2 < nkb) load_block(L0, it + 2);
+                store_block(L1, it + 1);
+            }
+        }
+    } else if (warp < 8) {
         // ------------------------------- transposing producers --------------------------------------
         for (int it = 0; it < nkb; ++it) {
             const int s = it & 1;
@@ -456,7 +775,7 @@ cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int
     const int maxs = (nblocks + 7) / 8;                  // ... but at least 8 row blocks each: a tile's epilogue is up to 32 K atomics
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
-    TnArgs g{A, lda, Mreal, B, ldb, Nreal, C, ldc, rows};
+    TnArgs g{A, lda, Mreal, B, ldb, Nreal, C, ldc, rows, EpGen{}};
     dim3 grid(splits, mt, nt);
     if (bn == 256) tn_tc_kernel<256><<<grid, DW_THREADS, dw_smem_bytes(256), s>>>(g);
     else if (bn == 128) tn_tc_kernel<128><<<grid, DW_THREADS, dw_smem_bytes(128), s>>>(g);
@@ -466,6 +785,18 @@ cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int
 
 cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s) {
     return launch_tn_tc(dap, FC1, FC1, ep, READS, READS, dW1, READS, rows, 256, num_sms, s);
+}
+
+// dW1 = dap^T ep with ep rebuilt from (codes, keep bits): one 100 x 200 tile, the row range split over every SM
+cudaError_t launch_dw1_gen(const float* dap, EpGen gen, float* dW1, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int nblocks = (rows + T_BK - 1) / T_BK;
+    int splits = num_sms;
+    const int maxs = (nblocks + 7) / 8;
+    if (splits > maxs) splits = maxs;
+    TnArgs g{dap, FC1, FC1, nullptr, READS, READS, dW1, READS, rows, gen};
+    tn_tc_kernel<256, 1><<<dim3(splits, 1, 1), DW_THREADS, dw_smem_bytes(256), s>>>(g);
+    return cudaGetLastError();
 }
 
 // ---- weight images -------------------------------------------------------------------------------------
@@ -543,6 +874,14 @@ cudaError_t train_tc_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(256));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tn_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(256));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_stream_kernel<FC1_BN, FC1_KB, 1, READS, READS, FC1, FC1, TEPI_FC1, 1>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(FC1_BN));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_DE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(128));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_stream_kernel<DIN_BN, DIN_KB, 2, GI_N, GI_N, IN0, IN0P, TEPI_STORE>,
@@ -569,11 +908,11 @@ cudaError_t launch_din_tc(int l, const float* dgi, const float* img, float* din,
     if (l == 0) {
         const int ntiles = mt * 2, grid = ntiles < num_sms ? ntiles : num_sms;
         tc_stream_kernel<DIN_BN, DIN_KB, 2, GI_N, GI_N, IN0, IN0P, TEPI_STORE>
-            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(0), nullptr, din, rows, ntiles, none);
+            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(0), nullptr, din, rows, ntiles, none, EpGen{});
     } else {
         const int grid = mt < num_sms ? mt : num_sms;
         tc_stream_kernel<DIN_BN, DIN_KB, 1, GI_N, GI_N, OUT_W, OUT_W, TEPI_STORE>
-            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(l), nullptr, din, rows, mt, none);
+            <<<grid, T_THREADS, t_smem_bytes(DIN_BN), s>>>(dgi, img + din_img_off(l), nullptr, din, rows, mt, none, EpGen{});
     }
     return cudaGetLastError();
 }
@@ -585,7 +924,7 @@ cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, fl
     const int ntiles = (rows + T_BM - 1) / T_BM;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     tc_stream_kernel<FC1_BN, FC1_KB, 1, READS, READS, FC1, FC1, TEPI_FC1>
-        <<<grid, T_THREADS, t_smem_bytes(FC1_BN), s>>>(ep, img, b1, a1, rows, ntiles, d);
+        <<<grid, T_THREADS, t_smem_bytes(FC1_BN), s>>>(ep, img, b1, a1, rows, ntiles, d, EpGen{});
     return cudaGetLastError();
 }
 
@@ -596,7 +935,28 @@ cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int ro
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     DropCfg none{0ull, 0u, 1.f};
     tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_STORE>
-        <<<grid, T_THREADS, t_smem_bytes(DEP_BN), s>>>(dap, img + IMG_FC1_FLOATS, nullptr, dep, rows, ntiles, none);
+        <<<grid, T_THREADS, t_smem_bytes(DEP_BN), s>>>(dap, img + IMG_FC1_FLOATS, nullptr, dep, rows, ntiles, none, EpGen{});
+    return cudaGetLastError();
+}
+
+// a1 = dropout(relu(ep W1^T + b1)) with ep rebuilt from (codes, keep bits)
+cudaError_t launch_fc1_gen(EpGen gen, const float* img, const float* b1, float* a1, int rows, DropCfg d, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int ntiles = (rows + T_BM - 1) / T_BM;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    tc_stream_kernel<FC1_BN, FC1_KB, 1, READS, READS, FC1, FC1, TEPI_FC1, 1>
+        <<<grid, T_THREADS, t_smem_bytes(FC1_BN), s>>>(nullptr, img, b1, a1, rows, ntiles, d, gen);
+    return cudaGetLastError();
+}
+
+// dE += scale * sum over kept (row, read) of (dap W1)[row][read], filed by the read's code: d(ep) never leaves the SM
+cudaError_t launch_dep_de(const float* dap, const float* img, EpGen gen, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const int ntiles = (rows + T_BM - 1) / T_BM;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    DropCfg none{0ull, 0u, 1.f};
+    tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_DE>
+        <<<grid, T_THREADS, t_smem_bytes(DEP_BN), s>>>(dap, img + IMG_FC1_FLOATS, nullptr, nullptr, rows, ntiles, none, gen);
     return cudaGetLastError();
 }
 

@@ -22,7 +22,7 @@ RELU_MARGIN = 1.5e-6   # ReLU pre-activations of the test inputs clear fp32 nois
 # Inputs found offline (oracle only) whose float64 ReLU pre-activations all keep RELU_MARGIN from 0; nearer
 # ones make any two implementations disagree on a ReLU derivative, which moves a few entries by ~1e-3.
 CLEAR_SEEDS = {1: 7126, 2: 7217, 5: 7515}                       # batch -> structured_windows seed, dropout off
-CLEAR_DROPOUT = {2: (7236, 16236), 3: (7446, 16446)}            # batch -> (input seed, mask seed), p = 0.2
+CLEAR_DROPOUT = {2: (8214, 17328), 3: (11980, 22123)}           # batch -> (input seed, mask seed), p = 0.2
 
 
 def _loss(model, x, y, seed=None):

@@ -103,7 +103,8 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
     constexpr int NS = t_stages(BN);                       // operand pipeline depth
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
     extern __shared__ unsigned char t_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment as an OFFSET into the shared array: the pointer keeps its address space (LDS / STS, not generic LD / ST)
+    unsigned char* smem = t_smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(t_smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     float* epi_stage = reinterpret_cast<float*>(smem + NS * STAGE + 256);
@@ -530,7 +531,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     constexpr int STAGE = dw_stage_bytes(BN);
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
     extern __shared__ unsigned char t_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment as an OFFSET into the shared array: the pointer keeps its address space (LDS / STS, not generic LD / ST)
+    unsigned char* smem = t_smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(t_smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const uint32_t sbase = t_smem_u32(smem);

@@ -602,7 +602,7 @@ def train_steps(dev, batch, steps, warmup, world=1, seed=0):
     model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(dev).train()
     if world > 1:
         rdist.broadcast_weights(model, src=0)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)      # as roko_b200/train.py creates it
     g = torch.Generator(device=dev).manual_seed(77 + seed)
     pool = 8                                                   # 8 x 2.3 MB inputs; activations (1 GB) dwarf L2 anyway
     xs = torch.randint(0, 12, (pool, batch, READS, COLS), dtype=torch.uint8, device=dev, generator=g)

@@ -18,7 +18,7 @@ struct roko_b200_model {
     float* raw_stage = nullptr;     // device copy of the raw (state_dict order) weights; the training backward reads them
     float* raw_al = nullptr;        // the same with 2 floats of padding before the GRU section: every tensor 16-byte aligned
     float* train_img = nullptr;     // tf32 hi / lo images of fc1.weight for the tcgen05 training products (train_tc.cu)
-    int train_tc = 5;               // ROKO_B200_TRAIN_TC: which training products run on tcgen05 (train_tc.cu) instead of the
+    int train_tc = 6;               // ROKO_B200_TRAIN_TC: which training products run on tcgen05 (train_tc.cu) instead of the
                                     // generic GEMM: >= 1 fc1 and d(ep), >= 2 dW1, >= 3 the GRU d(in), >= 4 dW_ih / dW_hh
                                     // (4 is measured slower: 11 520-row reductions leave too little work per 32 K-atomic tile epilogue)
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11

@@ -92,8 +92,8 @@ fc2_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ W2, const
 // of the 64-row tile: per row one a1 value, the row's 10 dg (broadcast), 20 FMA.
 __global__ void __launch_bounds__(TR_THREADS)
 fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float* __restrict__ a1,
-               const float* __restrict__ W2, float* __restrict__ dW2, float* __restrict__ db2, int rows50,
-               float scale) {
+               const float* __restrict__ W2, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ db1,
+               int rows50, float scale) {
     __shared__ float as[F2_ROWS][FC1];
     __shared__ __align__(16) float dgs[F2_ROWS][12];        // 10 used, padded for LDS.128
     const int tid = threadIdx.x, j = tid & 127, half = tid >> 7;
@@ -101,7 +101,7 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
     float w2c[FC2], accw[FC2];
 #pragma unroll
     for (int k = 0; k < FC2; ++k) { w2c[k] = active ? W2[k * FC1 + j] : 0.f; accw[k] = 0.f; }
-    float accb = 0.f;
+    float accb = 0.f, accd = 0.f;                           // db2 partial (threads 0..9), db1[j] partial: column sum of d(a1)
     const int ntiles = (rows50 + F2_ROWS - 1) / F2_ROWS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * F2_ROWS;
@@ -138,13 +138,16 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
                     accw[k] = fmaf(dg[k], a, accw[k]);
                     da = fmaf(dg[k], w2c[k], da);
                 }
-                if (row < nrow) a1[(size_t)(row0 + row) * FC1 + j] = a > 0.f ? da * scale : 0.f;
+                const float dpre = a > 0.f ? da * scale : 0.f;     // rows past the end hold a = 0
+                accd += dpre;
+                if (row < nrow) a1[(size_t)(row0 + row) * FC1 + j] = dpre;
             }
         }
     }
     if (active) {
 #pragma unroll
         for (int k = 0; k < FC2; ++k) atomicAdd(dW2 + k * FC1 + j, accw[k]);
+        if (db1) atomicAdd(db1 + j, accd);
     }
     if (tid < FC2) atomicAdd(db2 + tid, accb);
 }
@@ -307,12 +310,12 @@ cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, fl
     return cudaGetLastError();
 }
 
-cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2,
+cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2, float* db1,
                            int rows50, float scale, int num_sms, cudaStream_t s) {
     if (rows50 <= 0) return cudaSuccess;
     const int ntiles = (rows50 + F2_ROWS - 1) / F2_ROWS;
     const int grid = ntiles < 4 * num_sms ? ntiles : 4 * num_sms;
-    fc2_bwd_kernel<<<grid, TR_THREADS, 0, s>>>(du, u, a1_dap, W2, dW2, db2, rows50, scale);
+    fc2_bwd_kernel<<<grid, TR_THREADS, 0, s>>>(du, u, a1_dap, W2, dW2, db2, db1, rows50, scale);
     return cudaGetLastError();
 }
 

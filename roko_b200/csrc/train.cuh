@@ -61,7 +61,8 @@ cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint3
                               DropCfg d, int* status, cudaStream_t s);
 cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, float* u, int rows50, DropCfg d,
                            cudaStream_t s);
-cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2,
+// a1_dap: a1 in, d(fc1 pre-activation) out (in place); db1 += its column sums
+cudaError_t launch_fc2_bwd(const float* du, const float* u, float* a1_dap, const float* W2, float* dW2, float* db2, float* db1,
                            int rows50, float scale, int num_sms, cudaStream_t s);
 cudaError_t launch_drop_apply(const float* in, float* out, size_t n, unsigned int site, DropCfg d, cudaStream_t s);
 cudaError_t launch_colsum(const float* A, int lda, int rows, int ncols, float* out, cudaStream_t s);

@@ -167,7 +167,7 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         TCU(launch_rec_bwd(w.dh, reinterpret_cast<const float4*>(w.gates[l]), w.out[l], raw + raw_whh(l, 0),
                            (size_t)raw_dir_size(l), dgi, w.dghn, w.dghp, n_windows, sms, s));
         for (int dir = 0; dir < 2; ++dir) {
-            if (m->train_tc == 4) {                       // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
+            if (m->train_tc == 4 || m->train_tc >= 6) {   // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
                 TCU(launch_tn_tc(dgi + dir * G3, GI_N, G3, in, in_ld, in_w, grad_raw + raw_wih(l, dir), in_w, rows, 256, sms, s));
                 TCU(launch_tn_tc(w.dghp + dir * G3, GI_N, G3, w.out[l] + dir * HID, OUT_W, HID, grad_raw + raw_whh(l, dir), HID,
                                  rows, 128, sms, s));
@@ -198,7 +198,7 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
             TCU(launch_drop_apply(w.din, w.dh, (size_t)rows * OUT_W, DROP_GRU0 + (l - 1), d, s));
     }
     // front end: fc2, fc1, embedding
-    TCU(launch_fc2_bwd(w.din, w.u, w.a1, raw + RAW_W2, grad_raw + RAW_W2, grad_raw + RAW_B2, rows50, d.scale, sms, s));
+    TCU(launch_fc2_bwd(w.din, w.u, w.a1, raw + RAW_W2, grad_raw + RAW_W2, grad_raw + RAW_B2, grad_raw + RAW_B1, rows50, d.scale, sms, s));
     {
         const bool gen_ep = m->train_tc >= 5;
         const EpGen gen{w.xt, w.bits, w.bitsT, raw + RAW_E, d.scale, grad_raw + RAW_E};
@@ -212,7 +212,6 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
             a.M = FC1; a.N = READS; a.K = rows50;
             TCU(launch_gemm(a, false, false, EPI_ATOMIC, 0, sms, s));
         }
-        TCU(launch_colsum(w.a1, FC1, rows50, FC1, grad_raw + RAW_B1, s));
         if (gen_ep) {                                     // dE straight from the d(ep) = dap W1 tiles
             TCU(launch_dep_de(w.a1, m->train_img, gen, rows50, sms, s));
             return ROKO_B200_OK;

@@ -507,11 +507,11 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
 // ---- C += A^T B for row-major A [rows][lda], B [rows][ldb]: the weight-gradient products -----------------
 // (dW1 = dap^T ep over 576 000 rows; dW_ih = dgi^T in and dW_hh = dgh^T out over 11 520 rows per layer.)
 // Both operands have the REDUCTION index as the row, i.e. the transpose of what a K-major UMMA operand wants.
-// Eight producer warps transpose 32-row blocks on the fly: lane = k (row inside the block), one float4 of 4
-// output rows per task, written as 4 + 4 scalars (tf32 hi / lo) into the swizzled K-major images -- for a fixed
-// output row the 32 lanes fill exactly one 128-byte swizzle row, so the stores are conflict free.  A CTA owns
-// one 128 x BN output tile (blockIdx.y, blockIdx.z) and a contiguous range of row blocks (blockIdx.x of
-// gridDim.x splits), accumulates in TMEM and adds its tile to global memory once at the end.
+// Eight producer warps build the images of one 32-row block at a time: a thread takes (output column, 4 consecutive
+// rows), so the transposition happens in the loads (4-byte, lanes on consecutive columns: coalesced) and each image
+// gets one 16-byte store (tf32 hi / lo).  A CTA owns one 128 x BN output tile (blockIdx.y, blockIdx.z) and a contiguous
+// range of row blocks (blockIdx.x of gridDim.x splits), accumulates in TMEM and adds its tile to global memory once at
+// the end (staged through shared memory: row-contiguous atomics).
 struct TnArgs {
     const float* A; int lda; int Mreal;
     const float* B; int ldb; int Nreal;
@@ -522,7 +522,6 @@ struct TnArgs {
 constexpr int DW_THREADS = 288;                        // 8 producer warps (0-3 also epilogue) + 1 MMA warp
 __host__ __device__ constexpr int dw_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
 __host__ __device__ constexpr int dw_smem_bytes(int bn) { return 2 * dw_stage_bytes(bn) + 1024 + 256; }
-constexpr int DW_MAXT = 12;                            // tasks per producer warp: (128 + 256) / 4 quads over 8 warps
 
 template <int BN, int BGEN = 0>
 __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
@@ -543,7 +542,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     const int m0 = blockIdx.y * T_BM, n0 = blockIdx.z * BN;
     const int ma = (g.Mreal - m0) < T_BM ? (g.Mreal - m0) : T_BM;        // rows / columns of this tile that exist
     const int nb = (g.Nreal - n0) < BN ? (g.Nreal - n0) : BN;
-    const int qa = ma >> 2, ntasks = qa + (nb >> 2);
     // this CTA's range of 32-row blocks
     const int nblocks = (g.rows + T_BK - 1) / T_BK;
     const int per = (nblocks + gridDim.x - 1) / gridDim.x;
@@ -669,43 +667,74 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
             }
         }
     } else if (warp < 8) {
-        // ------------------------------- transposing producers --------------------------------------
-        for (int it = 0; it < nkb; ++it) {
-            const int s = it & 1;
-            const int row = (kb0 + it) * T_BK + lane;              // lane = k inside the block
-            const bool rv = row < g.rows;
-            float4 v[DW_MAXT];
+        // ------------------------------- producers, both operands loaded ------------------------------
+        // A and B are row-major with the reduction index as the row, the transpose of a K-major image.  Thread = (column
+        // c, 4 consecutive rows): four 4-byte loads with lanes on consecutive columns (coalesced), then ONE 16-byte store
+        // per image -- no scalar transposing stores.  Loads of block it + 1 are issued before block it is stored.
+        constexpr int NA = T_BM * 8 / 256, NB = BN * 8 / 256;          // 4 and 4 / 8 tasks per thread
+        int a_off[NA], a_k[NA], b_off[NB], b_k[NB];
+        const float* a_ptr[NA];
+        const float* b_ptr[NB];
 #pragma unroll
-            for (int i = 0; i < DW_MAXT; ++i) {
-                const int t = warp + 8 * i;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < ntasks && rv)
-                    v[i] = t < qa ? __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + m0 + 4 * t))
-                                  : __ldg(reinterpret_cast<const float4*>(g.B + (size_t)row * g.ldb + n0 + 4 * (t - qa)));
-            }
+        for (int u = 0; u < NA; ++u) {
+            const int task = tid + 256 * u, kq = task / T_BM, c = task - kq * T_BM;
+            a_k[u] = c < ma ? 4 * kq : (1 << 28);                        // columns past the tile fail every row test
+            a_off[u] = (c >> 3) * 1024 + (c & 7) * 128 + ((kq ^ (c & 7)) << 4);
+            a_ptr[u] = g.A + ((size_t)kb0 * T_BK + 4 * kq) * g.lda + m0 + c;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int task = tid + 256 * u, kq = task / BN, c = task - kq * BN;
+            b_k[u] = c < nb ? 4 * kq : (1 << 28);
+            b_off[u] = 2 * T_A_IMG + (c >> 3) * 1024 + (c & 7) * 128 + ((kq ^ (c & 7)) << 4);
+            b_ptr[u] = g.B + ((size_t)kb0 * T_BK + 4 * kq) * g.ldb + n0 + c;
+        }
+        struct Loads { float a[NA][4]; float b[NB][4]; };
+        auto load_block = [&](Loads& L, int it) {
+            const int k0 = (kb0 + it) * T_BK;
+#pragma unroll
+            for (int u = 0; u < NA; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    L.a[u][i] = (k0 + a_k[u] + i < g.rows) ? __ldg(a_ptr[u] + ((size_t)it * T_BK + i) * g.lda) : 0.f;
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    L.b[u][i] = (k0 + b_k[u] + i < g.rows) ? __ldg(b_ptr[u] + ((size_t)it * T_BK + i) * g.ldb) : 0.f;
+        };
+        auto split_store = [&](unsigned char* hi, unsigned char* lo, const float (&v)[4]) {
+            float4 h, l;
+            h.x = t_tf32_hi(v[0]); l.x = v[0] - h.x;
+            h.y = t_tf32_hi(v[1]); l.y = v[1] - h.y;
+            h.z = t_tf32_hi(v[2]); l.z = v[2] - h.z;
+            h.w = t_tf32_hi(v[3]); l.w = v[3] - h.w;
+            *reinterpret_cast<float4*>(hi) = h;
+            *reinterpret_cast<float4*>(lo) = l;
+        };
+        auto store_block = [&](const Loads& L, int it) {
+            const int s = it & 1;
             t_mbar_wait(BAR(2 + s), ((it >> 1) & 1) ^ 1);
             unsigned char* st = smem + s * STAGE;
 #pragma unroll
-            for (int i = 0; i < DW_MAXT; ++i) {
-                const int t = warp + 8 * i;
-                if (t < ntasks) {
-                    const bool isA = t < qa;
-                    unsigned char* hi = st + (isA ? 0 : 2 * T_A_IMG);
-                    unsigned char* lo = hi + (isA ? T_A_IMG : W_IMG);
-                    const int r0 = 4 * (isA ? t : t - qa);
-                    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            for (int u = 0; u < NA; ++u)
+                if (a_k[u] < T_BK) split_store(st + a_off[u], st + T_A_IMG + a_off[u], L.a[u]);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int n = r0 + c;
-                        const int off = (n >> 3) * 1024 + (n & 7) * 128 + (((lane >> 2) ^ (n & 7)) << 4) + (lane & 3) * 4;
-                        const float h = t_tf32_hi(e[c]);
-                        *reinterpret_cast<float*>(hi + off) = h;
-                        *reinterpret_cast<float*>(lo + off) = e[c] - h;
-                    }
-                }
-            }
+            for (int u = 0; u < NB; ++u)
+                if (b_k[u] < T_BK) split_store(st + b_off[u], st + W_IMG + b_off[u], L.b[u]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             t_mbar_arrive(BAR(s));
+        };
+        Loads L0, L1;
+        if (nkb > 0) load_block(L0, 0);
+#pragma unroll 1
+        for (int it = 0; it < nkb; it += 2) {
+            if (it + 1 < nkb) load_block(L1, it + 1);
+            store_block(L0, it);
+            if (it + 1 < nkb) {
+                if (it + 2 < nkb) load_block(L0, it + 2);
+                store_block(L1, it + 1);
+            }
         }
     } else {
         // ------------------------------- MMA issuer (whole warp, uniform) ---------------------------
@@ -732,11 +761,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     }
     if (warp < 4 && nkb > 0) {
         // ------------------------------- epilogue: TMEM -> global adds ------------------------------
+        // 32-column chunks go through shared memory (the operand stages are free once the last MMA has completed) so that
+        // a warp's 32 atomics of one instruction hit 128 consecutive bytes of one row instead of 32 different rows.
         t_mbar_wait(BAR(4), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int j = warp * 32 + lane;                              // TMEM lane == row inside the tile
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
-        float* crow = g.C + (size_t)(m0 + j) * g.ldc + n0;
+        float* T = reinterpret_cast<float*>(smem) + warp * 32 * T_EPI_ROW;
+        const int mrows = ma - warp * 32;                            // rows of this warp's quarter that exist
 #pragma unroll 1
         for (int c0 = 0; c0 < nb; c0 += 32) {
             uint32_t r[32];
@@ -750,11 +781,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (j < ma) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < nb) atomicAdd(crow + c0 + i, __uint_as_float(r[i]));
+            for (int qq = 0; qq < 8; ++qq)
+                *reinterpret_cast<float4*>(T + lane * T_EPI_ROW + qq * 4) =
+                    make_float4(__uint_as_float(r[qq * 4 + 0]), __uint_as_float(r[qq * 4 + 1]),
+                                __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
+            __syncwarp();
+            if (c0 + lane < nb) {
+                float* cc = g.C + (size_t)(m0 + warp * 32) * g.ldc + n0 + c0 + lane;
+#pragma unroll 4
+                for (int row = 0; row < 32; ++row)
+                    if (row < mrows) atomicAdd(cc + (size_t)row * g.ldc, T[row * T_EPI_ROW + lane]);
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -765,12 +804,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     }
 }
 
-// C[Mreal][Nreal] (row stride ldc, zeroed or holding earlier partial sums) += A^T B.  Mreal, Nreal, lda, ldb
-// multiples of 4, A and B 16-byte aligned.  bn = 128 or 256: the tile width.
+// C[Mreal][Nreal] (row stride ldc, zeroed or holding earlier partial sums) += A^T B.  bn = 128 or 256: the tile width.
 cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
                          int rows, int bn, int num_sms, cudaStream_t s) {
     if (rows <= 0 || Mreal <= 0 || Nreal <= 0) return cudaSuccess;
-    if ((lda | ldb | Mreal | Nreal) & 3) return cudaErrorInvalidValue;
     const int mt = (Mreal + T_BM - 1) / T_BM, nt = (Nreal + bn - 1) / bn;
     const int nblocks = (rows + T_BK - 1) / T_BK;
     int splits = num_sms / (mt * nt);                    // about one CTA per SM ...

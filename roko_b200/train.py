@@ -278,7 +278,8 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
         model = RNN(IN_SIZE, HIDDEN_SIZE, NUM_LAYERS).to(device)          # raises without a B200: no CPU path
     if world > 1:
         rdist.broadcast_weights(model, src=0)                               # same start and same shuffles everywhere
-    optim = torch.optim.Adam(model.parameters(), lr=lr)
+    # the reference's Adam (train.py:43); on a GPU the single-kernel (fused) implementation of the same update
+    optim = torch.optim.Adam(model.parameters(), lr=lr, fused=device.type == "cuda")
     stopper, saver = EarlyStopping(patience), BestCheckpoint(out) if rank == 0 else None
     log(f"Device: {device}  ranks: {world}  train windows: {len(train_ds)}"
         + (f"  val windows: {len(val_ds)}" if val_ds is not None else ""))

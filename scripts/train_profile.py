@@ -15,7 +15,7 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 torch.manual_seed(0)
 m = RM.RNN(500, 128, 3).to("cuda:0").train()
-opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
 x = torch.from_numpy(uniform_windows(batch, seed=3)).cuda()
 y = torch.randint(0, 5, (batch, 90), device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

@@ -62,7 +62,7 @@ print("OK")
 
 @pytest.mark.parametrize("env", [
     {"ROKO_B200_REC_NB": "2"}, {"ROKO_B200_REC_NB": "4"}, {"ROKO_B200_PROJ": "ffma"}, {"ROKO_B200_PROJ": "tf32"},
-    {"ROKO_B200_TRAIN_TC": "4"}, {"ROKO_B200_TRAIN_TC": "3"}, {"ROKO_B200_TRAIN_TC": "2"}, {"ROKO_B200_TRAIN_TC": "1"}, {"ROKO_B200_TRAIN_TC": "0"}, {"ROKO_B200_TRAIN_TC": "0", "ROKO_B200_GEMM_NOSTREAM": "1"},
+    {"ROKO_B200_TRAIN_TC": "6"}, {"ROKO_B200_TRAIN_TC": "4"}, {"ROKO_B200_TRAIN_TC": "3"}, {"ROKO_B200_TRAIN_TC": "2"}, {"ROKO_B200_TRAIN_TC": "1"}, {"ROKO_B200_TRAIN_TC": "0"}, {"ROKO_B200_TRAIN_TC": "0", "ROKO_B200_GEMM_NOSTREAM": "1"},
 ], ids=lambda e: ",".join(f"{k.replace('ROKO_B200_', '')}={v}" for k, v in e.items()))
 def test_training_kernel_variant(env):
     """The recurrence's window-group sizes (forward with saved gates, and backward) and the projection

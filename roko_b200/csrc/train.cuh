@@ -89,7 +89,11 @@ cudaError_t train_tc_setup();
 cudaError_t launch_train_images(const float* raw, float* img, cudaStream_t s);
 cudaError_t launch_din_tc(int l, const float* dgi, const float* img, float* din, int rows, int num_sms, cudaStream_t s);
 cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
-                         int rows, int bn, int num_sms, cudaStream_t s);
+                         int rows, int num_sms, cudaStream_t s);
+struct TnTile;      // train_tc.cu: one 128 x <= 256 tile of a C += A^T B product
+// the weight gradients of GRU layer l (dW_ih, dW_hh, both directions) in one launch
+cudaError_t launch_gru_dw(int l, const float* dgi, const float* in, const float* dghp, const float* out, float* grad_raw,
+                          int rows, int num_sms, cudaStream_t s);
 cudaError_t launch_fc1_tc(const float* ep, const float* img, const float* b1, float* a1, int rows, DropCfg d,
                           int num_sms, cudaStream_t s);
 cudaError_t launch_dep_tc(const float* dap, const float* img, float* dep, int rows, int num_sms, cudaStream_t s);

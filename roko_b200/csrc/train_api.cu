@@ -166,11 +166,13 @@ int roko_b200_train_backward(roko_b200_model* m, const uint8_t* x, int n_windows
         const float* in = l == 0 ? w.u : w.outd[l - 1];
         TCU(launch_rec_bwd(w.dh, reinterpret_cast<const float4*>(w.gates[l]), w.out[l], raw + raw_whh(l, 0),
                            (size_t)raw_dir_size(l), dgi, w.dghn, w.dghp, n_windows, sms, s));
-        for (int dir = 0; dir < 2; ++dir) {
-            if (m->train_tc == 4 || m->train_tc >= 6) {   // dW_ih = dgi_d^T in ; dW_hh = dgh_prev_d^T out_d
-                TCU(launch_tn_tc(dgi + dir * G3, GI_N, G3, in, in_ld, in_w, grad_raw + raw_wih(l, dir), in_w, rows, 256, sms, s));
+        if (m->train_tc >= 6)                             // dW_ih, dW_hh of both directions: one tcgen05 launch per layer
+            TCU(launch_gru_dw(l, dgi, in, w.dghp, w.out[l], grad_raw, rows, sms, s));
+        for (int dir = 0; dir < 2 && m->train_tc < 6; ++dir) {
+            if (m->train_tc == 4) {                       // the same products, one launch each
+                TCU(launch_tn_tc(dgi + dir * G3, GI_N, G3, in, in_ld, in_w, grad_raw + raw_wih(l, dir), in_w, rows, sms, s));
                 TCU(launch_tn_tc(w.dghp + dir * G3, GI_N, G3, w.out[l] + dir * HID, OUT_W, HID, grad_raw + raw_whh(l, dir), HID,
-                                 rows, 128, sms, s));
+                                 rows, sms, s));
                 continue;
             }
             GemmArgs a{};                                 // dW_ih = dgi_d^T in

@@ -512,23 +512,36 @@ tc_stream_kernel(const float* __restrict__ A, const float* __restrict__ wimg, co
 // gets one 16-byte store (tf32 hi / lo).  A CTA owns one 128 x BN output tile (blockIdx.y, blockIdx.z) and a contiguous
 // range of row blocks (blockIdx.x of gridDim.x splits), accumulates in TMEM and adds its tile to global memory once at
 // the end (staged through shared memory: row-contiguous atomics).
+// One launch covers a LIST of such products over the same rows (blockIdx.y = tile): the six dW_ih and dW_hh tiles of both
+// directions of a GRU layer go out together, so the fixed cost per launch (operand-stage clearing, tensor-memory
+// allocation, the atomics of the tile epilogue) is paid once per layer and every CTA gets a longer row range.
+struct TnTile {                // C[ma][nb] += A[:, 0..ma)^T B[:, 0..nb): pointers already at the tile's first column / element
+    const float* A; const float* B; float* C;
+    int lda, ldb, ldc;
+    int ma, nb;                // <= 128, <= 256
+    int n_mma;                 // MMA width for this tile: 128 or 256 (>= nb)
+};
+constexpr int TN_MAX_TILES = 18;
 struct TnArgs {
-    const float* A; int lda; int Mreal;
-    const float* B; int ldb; int Nreal;
-    float* C; int ldc;
+    TnTile tile[TN_MAX_TILES];
     int rows;
-    EpGen gen;             // BGEN: B is the masked embedding (rows = (window, column, channel), 200 columns), rebuilt not loaded
+    EpGen gen;                 // BGEN: B is the masked embedding (rows = (window, column, channel), 200 columns), rebuilt not loaded
 };
 constexpr int DW_THREADS = 288;                        // 8 producer warps (0-3 also epilogue) + 1 MMA warp
 __host__ __device__ constexpr int dw_stage_bytes(int bn) { return 2 * T_A_IMG + 2 * bn * T_BK * 4; }
 __host__ __device__ constexpr int dw_smem_bytes(int bn) { return 2 * dw_stage_bytes(bn) + 1024 + 256; }
 
 template <int BN, int BGEN = 0>
-__global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
+__global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const __grid_constant__ TnArgs g) {
     __shared__ float Es[BGEN ? EP_VALUES : 1];             // E * scale
     constexpr int W_IMG = BN * T_BK * 4;
     constexpr int STAGE = dw_stage_bytes(BN);
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
+    const TnTile& tl_ = g.tile[blockIdx.y];
+    const float* const tA = tl_.A;
+    const float* const tB = tl_.B;
+    float* const tC = tl_.C;
+    const int lda = tl_.lda, ldb = tl_.ldb, ldc = tl_.ldc;
+    const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tl_.n_mma >> 3) << 17) | ((uint32_t)(T_BM >> 4) << 24);
     extern __shared__ unsigned char t_smem_raw[];
     // 1 KB alignment as an OFFSET into the shared array: the pointer keeps its address space (LDS / STS, not generic LD / ST)
     unsigned char* smem = t_smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(t_smem_raw) & 1023u)) & 1023u);
@@ -539,9 +552,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     auto BAR = [&](int i) { return bar0 + 8u * i; };       // full[s] = s, empty[s] = 2+s, acc_full = 4
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    const int m0 = blockIdx.y * T_BM, n0 = blockIdx.z * BN;
-    const int ma = (g.Mreal - m0) < T_BM ? (g.Mreal - m0) : T_BM;        // rows / columns of this tile that exist
-    const int nb = (g.Nreal - n0) < BN ? (g.Nreal - n0) : BN;
+    const int ma = tl_.ma, nb = tl_.nb;                                  // rows / columns of this tile that exist
     // this CTA's range of 32-row blocks
     const int nblocks = (g.rows + T_BK - 1) / T_BK;
     const int per = (nblocks + gridDim.x - 1) / gridDim.x;
@@ -584,7 +595,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
             const int task = tid + 256 * u, kq = task / FC1, j = task - kq * FC1;
             a_k[u] = task < FC1 * 8 ? 4 * kq : (1 << 28);              // out-of-range tasks fail every row test
             a_off[u] = (j >> 3) * 1024 + (j & 7) * 128 + (((kq & 7) ^ (j & 7)) << 4);
-            a_ptr[u] = g.A + ((size_t)kb0 * T_BK + 4 * (kq & 7)) * FC1 + j;
+            a_ptr[u] = tA + ((size_t)kb0 * T_BK + 4 * (kq & 7)) * FC1 + j;
         }
         const bool b_on = tid < READS;
         const int r = b_on ? tid : 0;
@@ -680,14 +691,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
             const int task = tid + 256 * u, kq = task / T_BM, c = task - kq * T_BM;
             a_k[u] = c < ma ? 4 * kq : (1 << 28);                        // columns past the tile fail every row test
             a_off[u] = (c >> 3) * 1024 + (c & 7) * 128 + ((kq ^ (c & 7)) << 4);
-            a_ptr[u] = g.A + ((size_t)kb0 * T_BK + 4 * kq) * g.lda + m0 + c;
+            a_ptr[u] = tA + ((size_t)kb0 * T_BK + 4 * kq) * lda + c;
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
             const int task = tid + 256 * u, kq = task / BN, c = task - kq * BN;
             b_k[u] = c < nb ? 4 * kq : (1 << 28);
             b_off[u] = 2 * T_A_IMG + (c >> 3) * 1024 + (c & 7) * 128 + ((kq ^ (c & 7)) << 4);
-            b_ptr[u] = g.B + ((size_t)kb0 * T_BK + 4 * kq) * g.ldb + n0 + c;
+            b_ptr[u] = tB + ((size_t)kb0 * T_BK + 4 * kq) * ldb + c;
         }
         struct Loads { float a[NA][4]; float b[NB][4]; };
         auto load_block = [&](Loads& L, int it) {
@@ -696,12 +707,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
             for (int u = 0; u < NA; ++u)
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    L.a[u][i] = (k0 + a_k[u] + i < g.rows) ? __ldg(a_ptr[u] + ((size_t)it * T_BK + i) * g.lda) : 0.f;
+                    L.a[u][i] = (k0 + a_k[u] + i < g.rows) ? __ldg(a_ptr[u] + ((size_t)it * T_BK + i) * lda) : 0.f;
 #pragma unroll
             for (int u = 0; u < NB; ++u)
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    L.b[u][i] = (k0 + b_k[u] + i < g.rows) ? __ldg(b_ptr[u] + ((size_t)it * T_BK + i) * g.ldb) : 0.f;
+                    L.b[u][i] = (k0 + b_k[u] + i < g.rows) ? __ldg(b_ptr[u] + ((size_t)it * T_BK + i) * ldb) : 0.f;
         };
         auto split_store = [&](unsigned char* hi, unsigned char* lo, const float (&v)[4]) {
             float4 h, l;
@@ -788,10 +799,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
                                 __uint_as_float(r[qq * 4 + 2]), __uint_as_float(r[qq * 4 + 3]));
             __syncwarp();
             if (c0 + lane < nb) {
-                float* cc = g.C + (size_t)(m0 + warp * 32) * g.ldc + n0 + c0 + lane;
+                float* cc = tC + (size_t)(warp * 32) * ldc + c0 + lane;
 #pragma unroll 4
                 for (int row = 0; row < 32; ++row)
-                    if (row < mrows) atomicAdd(cc + (size_t)row * g.ldc, T[row * T_EPI_ROW + lane]);
+                    if (row < mrows) atomicAdd(cc + (size_t)row * ldc, T[row * T_EPI_ROW + lane]);
             }
             __syncwarp();
         }
@@ -804,37 +815,76 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tn_tc_kernel(const TnArgs g) {
     }
 }
 
-// C[Mreal][Nreal] (row stride ldc, zeroed or holding earlier partial sums) += A^T B.  bn = 128 or 256: the tile width.
-cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
-                         int rows, int bn, int num_sms, cudaStream_t s) {
-    if (rows <= 0 || Mreal <= 0 || Nreal <= 0) return cudaSuccess;
-    const int mt = (Mreal + T_BM - 1) / T_BM, nt = (Nreal + bn - 1) / bn;
+static int tn_splits(int ntiles, int rows, int num_sms) {
     const int nblocks = (rows + T_BK - 1) / T_BK;
-    int splits = num_sms / (mt * nt);                    // about one CTA per SM ...
+    int splits = num_sms / ntiles;                       // about one CTA per SM ...
     const int maxs = (nblocks + 7) / 8;                  // ... but at least 8 row blocks each: a tile's epilogue is up to 32 K atomics
     if (splits > maxs) splits = maxs;
-    if (splits < 1) splits = 1;
-    TnArgs g{A, lda, Mreal, B, ldb, Nreal, C, ldc, rows, EpGen{}};
-    dim3 grid(splits, mt, nt);
-    if (bn == 256) tn_tc_kernel<256><<<grid, DW_THREADS, dw_smem_bytes(256), s>>>(g);
-    else if (bn == 128) tn_tc_kernel<128><<<grid, DW_THREADS, dw_smem_bytes(128), s>>>(g);
-    else return cudaErrorInvalidValue;
+    return splits < 1 ? 1 : splits;
+}
+
+// every tile: C (zeroed or holding earlier partial sums) += A^T B over the same `rows`
+cudaError_t launch_tn_tiles(const TnTile* tiles, int ntiles, int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0 || ntiles <= 0) return cudaSuccess;
+    if (ntiles > TN_MAX_TILES) return cudaErrorInvalidValue;
+    TnArgs g{};
+    for (int i = 0; i < ntiles; ++i) {
+        g.tile[i] = tiles[i];
+        if (tiles[i].ma < 1 || tiles[i].ma > T_BM || tiles[i].nb < 1 || tiles[i].nb > 256) return cudaErrorInvalidValue;
+        g.tile[i].n_mma = tiles[i].nb <= 128 ? 128 : 256;
+    }
+    g.rows = rows;
+    tn_tc_kernel<256><<<dim3(tn_splits(ntiles, rows, num_sms), ntiles), DW_THREADS, dw_smem_bytes(256), s>>>(g);
     return cudaGetLastError();
 }
 
+// C[Mreal][Nreal] (row stride ldc, zeroed or holding earlier partial sums) += A^T B
+cudaError_t launch_tn_tc(const float* A, int lda, int Mreal, const float* B, int ldb, int Nreal, float* C, int ldc,
+                         int rows, int num_sms, cudaStream_t s) {
+    if (rows <= 0 || Mreal <= 0 || Nreal <= 0) return cudaSuccess;
+    TnTile t[TN_MAX_TILES];
+    int n = 0;
+    for (int m0 = 0; m0 < Mreal; m0 += T_BM)
+        for (int n0 = 0; n0 < Nreal; n0 += 256) {
+            if (n == TN_MAX_TILES) return cudaErrorInvalidValue;
+            t[n++] = TnTile{A + m0, B + n0, C + (size_t)m0 * ldc + n0, lda, ldb, ldc,
+                            Mreal - m0 < T_BM ? Mreal - m0 : T_BM, Nreal - n0 < 256 ? Nreal - n0 : 256, 0};
+        }
+    return launch_tn_tiles(t, n, rows, num_sms, s);
+}
+
+// dW_ih = dgi_d^T in and dW_hh = dgh_prev_d^T out_d, both directions of GRU layer l: 12 (18 for layer 0) tiles, one launch
+cudaError_t launch_gru_dw(int l, const float* dgi, const float* in, const float* dghp, const float* out, float* grad_raw,
+                          int rows, int num_sms, cudaStream_t s) {
+    const int in_w = gru_in(l), in_ld = gru_inp(l);
+    TnTile t[TN_MAX_TILES];
+    int n = 0;
+    for (int dir = 0; dir < 2; ++dir)
+        for (int m0 = 0; m0 < G3; m0 += T_BM) {
+            for (int n0 = 0; n0 < in_w; n0 += 256) {
+                if (n == TN_MAX_TILES) return cudaErrorInvalidValue;
+                t[n++] = TnTile{dgi + dir * G3 + m0, in + n0, grad_raw + raw_wih(l, dir) + (size_t)m0 * in_w + n0, GI_N, in_ld, in_w,
+                                T_BM, in_w - n0 < 256 ? in_w - n0 : 256, 0};
+            }
+            if (n == TN_MAX_TILES) return cudaErrorInvalidValue;
+            t[n++] = TnTile{dghp + dir * G3 + m0, out + dir * HID, grad_raw + raw_whh(l, dir) + (size_t)m0 * HID, GI_N, OUT_W, HID,
+                            T_BM, HID, 0};
+        }
+    return launch_tn_tiles(t, n, rows, num_sms, s);
+}
+
 cudaError_t launch_dw1_tc(const float* dap, const float* ep, float* dW1, int rows, int num_sms, cudaStream_t s) {
-    return launch_tn_tc(dap, FC1, FC1, ep, READS, READS, dW1, READS, rows, 256, num_sms, s);
+    return launch_tn_tc(dap, FC1, FC1, ep, READS, READS, dW1, READS, rows, num_sms, s);
 }
 
 // dW1 = dap^T ep with ep rebuilt from (codes, keep bits): one 100 x 200 tile, the row range split over every SM
 cudaError_t launch_dw1_gen(const float* dap, EpGen gen, float* dW1, int rows, int num_sms, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
-    const int nblocks = (rows + T_BK - 1) / T_BK;
-    int splits = num_sms;
-    const int maxs = (nblocks + 7) / 8;
-    if (splits > maxs) splits = maxs;
-    TnArgs g{dap, FC1, FC1, nullptr, READS, READS, dW1, READS, rows, gen};
-    tn_tc_kernel<256, 1><<<dim3(splits, 1, 1), DW_THREADS, dw_smem_bytes(256), s>>>(g);
+    TnArgs g{};
+    g.tile[0] = TnTile{dap, nullptr, dW1, FC1, READS, READS, FC1, READS, 256};
+    g.rows = rows;
+    g.gen = gen;
+    tn_tc_kernel<256, 1><<<dim3(tn_splits(1, rows, num_sms), 1), DW_THREADS, dw_smem_bytes(256), s>>>(g);
     return cudaGetLastError();
 }
 
@@ -920,8 +970,6 @@ cudaError_t train_tc_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_stream_kernel<DEP_BN, DEP_KB, 1, FC1, FC1, READS, READS, TEPI_DE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DEP_BN));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem_bytes(128));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_stream_kernel<DIN_BN, DIN_KB, 2, GI_N, GI_N, IN0, IN0P, TEPI_STORE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem_bytes(DIN_BN));

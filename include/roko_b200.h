@@ -117,8 +117,10 @@ int roko_b200_measure_fp32_peak(int device, double* tflops);
  *   (rnn_model.py:29,32,35 and nn.GRU's inter-layer dropout :41) active with probability `p_drop`
  *   (0 turns them off: the eval-mode function, differentiable) and masks derived from `seed`.
  *   x (n_windows,200,90) uint8, logits (n_windows,90,5) fp32, both device.  n_windows <= 1024.
- *   `tws` (roko_b200_train_workspace_bytes(n_windows), about 8.1 MB per window, 16-byte aligned)
+ *   `tws` (roko_b200_train_workspace_bytes(n_windows), about 4.7 MB per window, 16-byte aligned)
  *   receives the saved activations; hand the same buffer, x, p_drop and seed to train_backward.
+ *   (The size follows the ROKO_B200_TRAIN_TC environment variable exactly as model creation does: the
+ *   A/B chains <= 4 keep the masked embedding, 3.6 MB per window more.)
  * train_backward: given dlogits = dLoss/dlogits (n_windows,90,5), writes the gradient of every
  *   parameter into grad_raw: 1 099 731 fp32 in state_dict order, the layout roko_b200_model_load reads.
  *   Consumes `tws` (one backward per forward).  The cross-entropy itself (train.py:52) stays with the caller.

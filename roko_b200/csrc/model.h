@@ -18,9 +18,11 @@ struct roko_b200_model {
     float* raw_stage = nullptr;     // device copy of the raw (state_dict order) weights; the training backward reads them
     float* raw_al = nullptr;        // the same with 2 floats of padding before the GRU section: every tensor 16-byte aligned
     float* train_img = nullptr;     // tf32 hi / lo images of fc1.weight for the tcgen05 training products (train_tc.cu)
-    int train_tc = 6;               // ROKO_B200_TRAIN_TC: which training products run on tcgen05 (train_tc.cu) instead of the
-                                    // generic GEMM: >= 1 fc1 and d(ep), >= 2 dW1, >= 3 the GRU d(in), >= 4 dW_ih / dW_hh
-                                    // (4 is measured slower: 11 520-row reductions leave too little work per 32 K-atomic tile epilogue)
+    static constexpr int TRAIN_TC_DEFAULT = 6;
+    int train_tc = TRAIN_TC_DEFAULT; // ROKO_B200_TRAIN_TC: which training products run on tcgen05 (train_tc.cu) instead of the
+                                    // generic GEMM: >= 1 fc1 and d(ep), >= 2 dW1, >= 3 the GRU d(in), 4 dW_ih / dW_hh (a launch
+                                    // per product), >= 5 the masked embedding is rebuilt in the consumers' producer warps, never
+                                    // stored, >= 6 dW_ih / dW_hh as one tile-list launch per layer (default)
     int* status = nullptr;          // device flag word, bit 0: code outside 0..11
     bool loaded = false;
     int use_tc = 4;                 // projection: 4 = tcgen05, fp16-split operands (proj_h.cu, default); 3 = tcgen05 3xTF32

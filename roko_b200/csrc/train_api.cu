@@ -3,6 +3,7 @@
 // run for roko/train.py:46-53, as chains of kernels on the caller's stream.  The caller owns one
 // scratch buffer that carries the saved activations from forward to backward.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/roko_b200.h"
 #include "model.h"
@@ -29,8 +30,19 @@ int tfail(int code, const char* fmt, const char* a = "") {
 constexpr int TRAIN_MAX_WINDOWS = 1024;
 constexpr size_t ROW_EP = (size_t)EMB * READS;       // per (window, column) row
 constexpr size_t ROW_A1 = (size_t)EMB * FC1;
-constexpr size_t ROW_FLOATS = ROW_EP + ROW_A1 + IN0P + GI_N + 3 * (2 * HID * 4) + 3 * OUT_W + 2 * OUT_W
+// per (window, column) row, without the materialised masked embedding (only the ROKO_B200_TRAIN_TC <= 4 chains keep one)
+constexpr size_t ROW_FLOATS = ROW_A1 + IN0P + GI_N + 3 * (2 * HID * 4) + 3 * OUT_W + 2 * OUT_W
                               + GI_N + OUT_W + OUT_W + IN0P + MASK_WORDS + MASKT_WORDS + READS / 4;
+
+bool keeps_ep(int train_tc) { return train_tc < 5; }
+int train_tc_from_env() {                                 // what a model created now would use (api.cu reads the same variable)
+    const char* tt = getenv("ROKO_B200_TRAIN_TC");
+    return tt ? atoi(tt) : roko_b200_model::TRAIN_TC_DEFAULT;
+}
+size_t ws_bytes(int n_windows, int train_tc) {
+    const size_t n = n_windows < 1 ? 1 : (size_t)n_windows;
+    return n * COLS * (ROW_FLOATS + (keeps_ep(train_tc) ? ROW_EP : 0)) * sizeof(float);
+}
 
 struct TrainWs {
     float *ep, *a1, *u, *gi, *gates[3], *out[3], *outd[2], *dghp, *dghn, *dh, *din;
@@ -42,7 +54,6 @@ struct TrainWs {
 TrainWs carve(void* base, size_t rows) {
     TrainWs w;
     float* p = static_cast<float*>(base);
-    w.ep = p; p += rows * ROW_EP;
     w.a1 = p; p += rows * ROW_A1;
     w.u = p; p += rows * IN0P;
     w.gi = p; p += rows * GI_N;
@@ -55,7 +66,8 @@ TrainWs carve(void* base, size_t rows) {
     w.din = p; p += rows * IN0P;
     w.bits = reinterpret_cast<uint32_t*>(p); p += rows * MASK_WORDS;
     w.bitsT = reinterpret_cast<uint32_t*>(p); p += rows * MASKT_WORDS;
-    w.xt = reinterpret_cast<uint8_t*>(p);
+    w.xt = reinterpret_cast<uint8_t*>(p); p += rows * (READS / 4);
+    w.ep = p;                                             // last: only there when the chain materialises it (keeps_ep)
     return w;
 }
 
@@ -73,7 +85,7 @@ int check_train(roko_b200_model* m, const void* x, int n, const void* tws, size_
     if (n < 1 || n > TRAIN_MAX_WINDOWS) return tfail(ROKO_B200_EARG, "training batch must hold 1..1024 windows%s");
     if (!x || !tws) return tfail(ROKO_B200_EARG, "x / workspace is NULL%s");
     if (((uintptr_t)x & 15) || ((uintptr_t)tws & 15)) return tfail(ROKO_B200_EARG, "x / workspace must be 16-byte aligned%s");
-    if (tws_bytes < roko_b200_train_workspace_bytes(n)) return tfail(ROKO_B200_EARG, "training workspace too small%s");
+    if (tws_bytes < ws_bytes(n, m->train_tc)) return tfail(ROKO_B200_EARG, "training workspace too small%s");
     return ROKO_B200_OK;
 }
 
@@ -87,10 +99,7 @@ struct DevGuard {
 
 extern "C" {
 
-size_t roko_b200_train_workspace_bytes(int n_windows) {
-    const size_t n = n_windows < 1 ? 1 : (size_t)n_windows;
-    return n * COLS * ROW_FLOATS * sizeof(float);
-}
+size_t roko_b200_train_workspace_bytes(int n_windows) { return ws_bytes(n_windows, train_tc_from_env()); }
 
 int roko_b200_train_forward(roko_b200_model* m, const uint8_t* x, int n_windows, float p_drop,
                             unsigned long long seed, float* logits, void* tws, size_t tws_bytes, void* stream) {

@@ -56,30 +56,51 @@ embed_drop_kernel(const uint8_t* __restrict__ x, const float* __restrict__ E, fl
 }
 
 // u[m][e*10+k] = dropout(relu(b2[k] + sum_j W2[k][j] a1[(m,e)][j]))   rnn_model.py:53-56
-constexpr int F2_ROWS = 64;
-__global__ void __launch_bounds__(TR_THREADS)
+// 96-row tiles staged with 16-byte loads; thread = (row, half of the 10 outputs): per 4 inputs one 16-byte read of its
+// row (lanes = consecutive rows: conflict free) and five broadcast 16-byte reads of W2 for 20 FMA.
+constexpr int F2_ROWS = 64;                                // fc2_bwd tile
+constexpr int F2F_ROWS = 96, F2F_THREADS = 2 * F2F_ROWS;
+__global__ void __launch_bounds__(F2F_THREADS)
 fc2_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ W2, const float* __restrict__ b2,
                float* __restrict__ u, int rows50, DropCfg d) {
-    __shared__ float as[F2_ROWS][FC1];
-    __shared__ float ws[FC2][FC1];
+    __shared__ __align__(16) float as[F2F_ROWS][FC1];
+    __shared__ __align__(16) float ws[FC2][FC1];
     __shared__ float bs[FC2];
-    const int tid = threadIdx.x, row0 = blockIdx.x * F2_ROWS;
-    for (int i = tid; i < FC2 * FC1; i += TR_THREADS) (&ws[0][0])[i] = W2[i];
+    const int tid = threadIdx.x, row0 = blockIdx.x * F2F_ROWS;
+    for (int i = tid; i < FC2 * FC1; i += F2F_THREADS) (&ws[0][0])[i] = W2[i];
     if (tid < FC2) bs[tid] = b2[tid];
-    const int nrow = (rows50 - row0) < F2_ROWS ? (rows50 - row0) : F2_ROWS;
-    for (int i = tid; i < F2_ROWS * FC1; i += TR_THREADS)
-        (&as[0][0])[i] = i < nrow * FC1 ? a1[(size_t)row0 * FC1 + i] : 0.f;
+    const int nrow = (rows50 - row0) < F2F_ROWS ? (rows50 - row0) : F2F_ROWS;
+    const float4* src = reinterpret_cast<const float4*>(a1 + (size_t)row0 * FC1);      // 96 * 100 floats per tile: 16-byte aligned
+    float4* dst = reinterpret_cast<float4*>(&as[0][0]);
+#pragma unroll
+    for (int it = 0; it < (F2F_ROWS * FC1 / 4 + F2F_THREADS - 1) / F2F_THREADS; ++it) {
+        const int i = tid + it * F2F_THREADS;
+        if (i < F2F_ROWS * FC1 / 4) dst[i] = i < nrow * (FC1 / 4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
-    const int row = tid >> 2, kq = tid & 3;
+    const int half = tid / F2F_ROWS, row = tid - half * F2F_ROWS, kb = half * (FC2 / 2);
     if (row < nrow) {
+        float acc[FC2 / 2];
+#pragma unroll
+        for (int k = 0; k < FC2 / 2; ++k) acc[k] = bs[kb + k];
+#pragma unroll 5
+        for (int q = 0; q < FC1 / 4; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(&as[row][4 * q]);
+#pragma unroll
+            for (int k = 0; k < FC2 / 2; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(&ws[kb + k][4 * q]);
+                acc[k] = fmaf(a.x, w.x, acc[k]);             // j ascending, as the scalar loop it replaces
+                acc[k] = fmaf(a.y, w.y, acc[k]);
+                acc[k] = fmaf(a.z, w.z, acc[k]);
+                acc[k] = fmaf(a.w, w.w, acc[k]);
+            }
+        }
         const int g = row0 + row, m = g / EMB, e = g - m * EMB;
-        for (int k = kq; k < FC2; k += 4) {
-            float acc = bs[k];
-#pragma unroll 4
-            for (int j = 0; j < FC1; ++j) acc = fmaf(as[row][j], ws[k][j], acc);
-            acc = fmaxf(acc, 0.f);
-            acc = drop_keep(d, DROP_FC2, (unsigned long long)g * FC2 + k) ? acc * d.scale : 0.f;
-            u[(size_t)m * IN0P + e * FC2 + k] = acc;
+#pragma unroll
+        for (int k = 0; k < FC2 / 2; ++k) {
+            float v = fmaxf(acc[k], 0.f);
+            v = drop_keep(d, DROP_FC2, (unsigned long long)g * FC2 + kb + k) ? v * d.scale : 0.f;
+            u[(size_t)m * IN0P + e * FC2 + kb + k] = v;
         }
     }
 }
@@ -94,7 +115,7 @@ __global__ void __launch_bounds__(TR_THREADS)
 fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float* __restrict__ a1,
                const float* __restrict__ W2, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ db1,
                int rows50, float scale) {
-    __shared__ float as[F2_ROWS][FC1];
+    __shared__ __align__(16) float as[F2_ROWS][FC1];
     __shared__ __align__(16) float dgs[F2_ROWS][12];        // 10 used, padded for LDS.128
     const int tid = threadIdx.x, j = tid & 127, half = tid >> 7;
     const bool active = j < FC1;
@@ -107,9 +128,15 @@ fc2_bwd_kernel(const float* __restrict__ du, const float* __restrict__ u, float*
         const int row0 = tile * F2_ROWS;
         const int nrow = (rows50 - row0) < F2_ROWS ? (rows50 - row0) : F2_ROWS;
         __syncthreads();                                    // previous tile's readers are done
-#pragma unroll 5
-        for (int i = tid; i < F2_ROWS * FC1; i += TR_THREADS)
-            (&as[0][0])[i] = i < nrow * FC1 ? a1[(size_t)row0 * FC1 + i] : 0.f;
+        {   // 64 * 100 floats per tile: 16-byte loads, all of a thread's 6-7 in flight
+            const float4* src = reinterpret_cast<const float4*>(a1 + (size_t)row0 * FC1);
+            float4* dst = reinterpret_cast<float4*>(&as[0][0]);
+#pragma unroll
+            for (int it = 0; it < (F2_ROWS * FC1 / 4 + TR_THREADS - 1) / TR_THREADS; ++it) {
+                const int i = tid + it * TR_THREADS;
+                if (i < F2_ROWS * FC1 / 4) dst[i] = i < nrow * (FC1 / 4) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         for (int i = tid; i < F2_ROWS * 12; i += TR_THREADS) {
             const int row = i / 12, k = i - row * 12;
             float v = 0.f;
@@ -306,7 +333,7 @@ cudaError_t launch_embed_drop(const uint8_t* x, const float* E, float* ep, uint3
 cudaError_t launch_fc2_fwd(const float* a1, const float* W2, const float* b2, float* u, int rows50, DropCfg d,
                            cudaStream_t s) {
     if (rows50 <= 0) return cudaSuccess;
-    fc2_fwd_kernel<<<(rows50 + F2_ROWS - 1) / F2_ROWS, TR_THREADS, 0, s>>>(a1, W2, b2, u, rows50, d);
+    fc2_fwd_kernel<<<(rows50 + F2F_ROWS - 1) / F2F_ROWS, F2F_THREADS, 0, s>>>(a1, W2, b2, u, rows50, d);
     return cudaGetLastError();
 }
 

@@ -21,4 +21,13 @@ ROKO_B200_GRAPHS=0 $T compute-sanitizer --tool memcheck --print-limit 20 python 
 echo "memcheck b5 rc=$?"; tail -n 2 gpurun_out/r02_memcheck_b5.log
 ROKO_B200_REC_TC_MIN=32 ROKO_B200_GRAPHS=0 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/profile_target.py 33 1 > gpurun_out/r02_racecheck_b33.log 2>&1
 echo "racecheck rc=$?"; tail -n 3 gpurun_out/r02_racecheck_b33.log
+# training step: launch list, event timings, sanitizers at a ragged small batch (3 windows = 105.5 row tiles)
+$T ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_train_launches.csv \
+    python scripts/train_profile.py 128 2 > /dev/null 2>&1
+echo "train launch list rc=$?"
+$T python scripts/train_profile.py 128 20 > gpurun_out/r02_train_profile.log 2>&1; tail -n 1 gpurun_out/r02_train_profile.log
+$T compute-sanitizer --tool memcheck --print-limit 20 python scripts/train_profile.py 3 1 > gpurun_out/r02_memcheck_train_b3.log 2>&1
+echo "memcheck train rc=$?"; tail -n 2 gpurun_out/r02_memcheck_train_b3.log
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python scripts/train_profile.py 2 1 > gpurun_out/r02_racecheck_train_b2.log 2>&1
+echo "racecheck train rc=$?"; tail -n 3 gpurun_out/r02_racecheck_train_b2.log
 ls -la gpurun_out | grep r02_

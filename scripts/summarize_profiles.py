@@ -131,10 +131,43 @@ def sanitizers():
     with open(os.path.join(OUT, f"{TAG}_sanitizers.md"), "w") as f:
         f.write(f"# compute-sanitizer ({TAG})\n\n`scripts/capture_profiles.sh`: `scripts/profile_target.py <batch> 1` under memcheck / racecheck, CUDA graphs off,\n"
                 "`ROKO_B200_REC_TC_MIN=32` for the 33 / 40-window runs (a ragged last 32-window group in `rec_h_kernel`; its clamped\n"
-                "`gi` reads stay inside the batch), default threshold for the 5-window run (register-resident FFMA recurrence).\n\n")
+                "`gi` reads stay inside the batch), default threshold for the 5-window run (register-resident FFMA recurrence).\n"
+                "`*_train_*`: three training steps (`scripts/train_profile.py <batch> 1`: forward with dropout, loss, backward, Adam).\n\n")
         for name in logs:
             body = open(os.path.join(SRC, name)).read().strip().splitlines()
             f.write(f"## {name}\n\n```\n" + "\n".join(body[-6:]) + "\n```\n\n")
+
+
+def train_launches():
+    """One training step's kernels (last step of scripts/train_profile.py under the ncu launch-list pass)."""
+    src = os.path.join(SRC, f"{TAG}_train_launches.csv")
+    if not os.path.exists(src):
+        return
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    launches = [(r[ki], float(r[vi].replace(",", "")) * (1e-3 if r[ui] == "ns" else 1.0)) for r in rows[1:]]
+    start = max(i for i, (k, _) in enumerate(launches) if "embed_drop" in k)
+    agg = collections.OrderedDict()
+    for k, v in launches[start:]:
+        k = re.sub(r"\(.*", "", k.replace("roko::", "").replace("void ", ""))
+        k = "torch:" + k.split("<")[0][:40] if k.startswith("at::") else k
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    total = sum(a[1] for a in agg.values())
+    events = ""
+    log = os.path.join(SRC, f"{TAG}_train_profile.log")
+    if os.path.exists(log):
+        events = open(log).read().strip().splitlines()[-1]
+    with open(os.path.join(OUT, f"{TAG}_train_launches.md"), "w") as f:
+        f.write(f"# ncu launch list of one training step ({TAG}): `scripts/train_profile.py 128 2` under `ncu --metrics gpu__time_duration.sum`\n\n"
+                "Last step of the run (from its `embed_drop_kernel` on): train-mode forward with dropout, cross-entropy, hand-written backward,\n"
+                "fused Adam, batch 128, default chain (`ROKO_B200_TRAIN_TC=6`).\n"
+                f"CUDA-event times of the same script without ncu (20 steps): {events}\n\n```\n")
+        for k, a in sorted(agg.items(), key=lambda t: -t[1][1]):
+            f.write(f"{a[1]:9.1f} us {100 * a[1] / total:5.1f}% {a[0]:3d}x  {k}\n")
+        f.write(f"total {total:.1f} us over {sum(a[0] for a in agg.values())} launches\n```\n")
 
 
 def sass():
@@ -170,6 +203,7 @@ def main():
     ncu_summaries()
     launch_list()
     sanitizers()
+    train_launches()
     sass()
     print("wrote", sorted(os.listdir(OUT)))
 

@@ -280,6 +280,8 @@ def train(train_path, out, val_path=None, mem=False, workers=0, batch_size=BATCH
         rdist.broadcast_weights(model, src=0)                               # same start and same shuffles everywhere
     # the reference's Adam (train.py:43); on a GPU the single-kernel (fused) implementation of the same update
     optim = torch.optim.Adam(model.parameters(), lr=lr, fused=device.type == "cuda")
+    if rank != 0:
+        log = lambda *a, **k: None                                          # one log, as the reference's single process writes
     stopper, saver = EarlyStopping(patience), BestCheckpoint(out) if rank == 0 else None
     log(f"Device: {device}  ranks: {world}  train windows: {len(train_ds)}"
         + (f"  val windows: {len(val_ds)}" if val_ds is not None else ""))

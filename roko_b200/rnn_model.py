@@ -35,7 +35,7 @@ NUM_LAYERS = 3
 
 READS, COLS, CLASSES = 200, 90, 5
 MAX_CHUNK = 2368          # windows per internal chunk = 148 SMs x 16 (bounds scratch: 0.66 MB / window)
-MAX_TRAIN_BATCH = 1024    # windows per training forward/backward (8.1 MB of saved activations each)
+MAX_TRAIN_BATCH = 1024    # windows per training forward/backward (4.7 MB of saved activations each)
 
 
 def gru_init(gru):

@@ -42,6 +42,18 @@ def test_geometry_queries(lib):
     assert lib.roko_b200_workspace_bytes(128) == 128 * per
 
 
+def test_training_scratch_follows_the_chain_selection(lib, monkeypatch):
+    """Default chain: no materialised masked embedding (4.7 MB of saved activations per window); the A/B chains
+    ROKO_B200_TRAIN_TC <= 4 keep it (200 x 90 x 50 fp32 more).  Same variable, same reading as model creation."""
+    monkeypatch.delenv("ROKO_B200_TRAIN_TC", raising=False)
+    per = lib.roko_b200_train_workspace_bytes(1)
+    assert 4.5e6 < per < 5.0e6 and lib.roko_b200_train_workspace_bytes(128) == 128 * per
+    monkeypatch.setenv("ROKO_B200_TRAIN_TC", "3")
+    assert lib.roko_b200_train_workspace_bytes(1) == per + 200 * 90 * 50 * 4
+    monkeypatch.setenv("ROKO_B200_TRAIN_TC", "6")
+    assert lib.roko_b200_train_workspace_bytes(1) == per
+
+
 def test_argument_errors_without_gpu(lib):
     from roko_b200 import _cabi
     assert lib.roko_b200_model_create(None, 0) == _cabi.EARG

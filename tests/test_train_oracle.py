@@ -40,6 +40,16 @@ def test_mask_restatement_statistics():
     assert all(np.array_equal(c[k][0], a[k][0]) for k in TO.SITES)
 
 
+def test_mask_restatement_known_answers():
+    """Pins the restatement of roko_b200/csrc/train.cuh:drop_hash (the GPU suite pins the kernels to the restatement)."""
+    m = TO.kernel_keep_masks(0.2, 20240921, 1)
+    head = {k: "".join(str(int(v)) for v in m[k].reshape(-1)[:48]) for k in ("emb", "fc1", "gru1")}
+    assert head == {"emb": "111011111111111101101111101011011110101011111111",
+                    "fc1": "110101001101110110111111110110101110111111011111",
+                    "gru1": "111111100101111111111101001111111111111101101111"}
+    assert (int(m["emb"].sum()), int(m["fc1"].sum()), int(m["gru1"].sum())) == (720556, 359650, 18406)
+
+
 def test_masked_forward_differs_and_scales(seed1_weights, train_golden):
     x, y = train_golden["x"][:1], train_golden["y"][:1]
     masks = TO.kernel_keep_masks(0.2, 3, 1)
